@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- the node2vec hot path on B200: walk-steps/s (+ SGNS pairs/s).
+
+Contract (see the task prompt): `python bench.py --gpus N --steps K --warmup W` prints ONE
+JSON line on rank 0.  A "step" is one pass of the hot path over one batch of synthetic
+input: every start vertex of the workload graph x num_walks walkers x walk_length steps
+(then, when the SGNS half is built, one SGNS epoch over those walks).
+
+  value     whole-job walk-steps/s with the graph already packed in HBM (kernel only)
+  e2e       the same metric through the public API (node2vec_b200.fugue.random_walk) with
+            HOST buffers: H2D of the arc list, CSR + alias build, walk, D2H of the walk matrix
+  roofline  HBM model of the walk kernel: achieved = steps/s * B_step(T, l) with the trial
+            and probe counts the kernel itself reports
+  cpu_baseline  the reference's algorithm (oracle port, test infrastructure) on the host cores
+
+`--impl reference` times the reference's own CPU path (oracle port) instead.
+Multi-GPU: walkers shard by start vertex with a replicated graph, no data-path collective
+(`"scaling": "weak"`: every rank walks the full per-GPU workload from its own start-vertex
+shard of an N-times larger walker set).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1] -- the largest configuration quoted on ONE B200
+    "blogcatalog_like": dict(graph="blogcatalog_like(10k vertices, 334k edges)", n=10000, m=334000,
+                             p=0.25, q=4.0, num_walks=80, walk_length=40, dim=128),
+    # BASELINE.json configs[0] -- the reference's own CPU-runnable case
+    "er_10k": dict(graph="erdos_renyi(10k vertices, 100k edges)", n=10000, m=100000,
+                   p=1.0, q=0.5, num_walks=10, walk_length=20, dim=128),
+}
+
+
+def make_graph(name):
+    from node2vec_b200 import synth
+    w = WORKLOADS[name]
+    if name == "blogcatalog_like":
+        return synth.blogcatalog_like(w["n"], w["m"], seed=42)
+    return synth.erdos_renyi(w["n"], w["m"], seed=42)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def walk_bytes_per_step(stats):
+    """16 B vertex record + T * (16 B arc record + 4 B * probes) + 4 B store.
+    (The arc record is 16 B here, not the 12 B of the survey's sketch.)"""
+    steps = max(stats["steps"], 1)
+    T = stats["trials"] / steps
+    probes_per_trial = stats["probes"] / max(stats["trials"], 1)
+    return 16.0 + T * (16.0 + 4.0 * probes_per_trial) + 4.0, T, probes_per_trial
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------
+def cpu_baseline_walk(name, budget_s=12.0, procs=None):
+    """The reference's algorithm on the host cores (oracle Python port: per walker per step
+    it re-derives the biased weights and rebuilds the alias table, exactly like
+    next_step_random_walk).  A bounded sample of the same workload: every process walks
+    seeded start vertices of the same graph (2 walkers each, full walk_length) until the
+    time budget is spent.  Adjacency construction is outside the timed region."""
+    import multiprocessing as mp
+    global _ADJ
+    from oracle import ref_walk
+    w = WORKLOADS[name]
+    src, dst = make_graph(name)
+    procs = procs or os.cpu_count() or 1
+    _ADJ = ref_walk.build_adjacency(src.tolist(), dst.tolist(), [1.0] * len(src))
+    rng = np.random.default_rng(0)
+    starts = rng.permutation(np.unique(src))
+    chunks = [c.tolist() for c in np.array_split(starts, procs) if len(c)]
+    args = [(c, 2, w["walk_length"], w["p"], w["q"], 1000 + i, budget_s) for i, c in enumerate(chunks)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(chunks)) as pool:
+        res = pool.map(_cpu_walk_chunk, args)
+    steps = int(sum(r[0] for r in res))
+    dt = max(r[1] for r in res)
+    n_starts = int(sum(r[2] for r in res))
+    return {"value": steps / dt, "unit": "walk-steps/s", "cores": len(chunks), "kind": "port",
+            "sample": f"{n_starts} start vertices x 2 walks x {w['walk_length']} steps = {steps} steps in {dt:.1f}s on "
+                      f"{len(chunks)} processes (oracle/ref_walk.py: the reference's per-row algorithm, "
+                      f"adjacency prebuilt, Fugue joins and pickle/base64 decoding not included)"}
+
+
+_ADJ = None
+
+
+def _cpu_walk_chunk(a):
+    import random
+    from oracle import ref_walk
+    starts, num_walks, L, p, q, seed, budget = a
+    rng = random.Random(seed)
+    steps = done = 0
+    t0 = time.perf_counter()
+    for v in starts:
+        rows = ref_walk.start_rows([v], num_walks)
+        for _ in range(L):
+            rows = [ref_walk.step_row(r, _ADJ, p, q, rng.random(), rng.random()) for r in rows if r["dst"] in _ADJ]
+        steps += len(rows) * L
+        done += 1
+        if time.perf_counter() - t0 > budget:
+            break
+    return steps, time.perf_counter() - t0, done
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port) for the same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    w = WORKLOADS[name]
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 3))):
+        base = cpu_baseline_walk(name)
+        vals.append(base["value"])
+    v = float(np.mean(vals))
+    steps_per_pass = len(np.unique(make_graph(name)[0])) * w["num_walks"] * w["walk_length"]
+    line = {
+        "impl": "reference", "metric": "walk_steps_per_s", "value": v, "unit": "walk-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * steps_per_pass / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, **{k: w[k] for k in ("graph", "p", "q", "num_walks", "walk_length")},
+                   "note": "ms_per_step extrapolates the sampled rate to one full pass"},
+        "cpu_baseline": {**base, "value": v},
+        "e2e": {"value": v, "unit": "walk-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="blogcatalog_like", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from node2vec_b200 import fugue
+    from node2vec_b200.graph import DeviceGraph
+    name = args.workload
+    w = WORKLOADS[name]
+    src, dst = make_graph(name)
+    g = DeviceGraph.from_arcs(src, dst, None, n_vertices=w["n"])
+    start = g.start_vertices()
+    # weak scaling: rank r walks the same number of walkers, from walk numbers
+    # [r*num_walks, (r+1)*num_walks) of every start vertex (disjoint Philox streams)
+    seed = 42 + 7919 * rank
+    W = int(start.numel()) * w["num_walks"]
+    steps_per_pass = W * w["walk_length"]
+    pitch = (w["walk_length"] + 1 + 7) // 8 * 8
+    out = torch.empty((W, pitch), dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def one_pass():
+        g.walk(start, w["num_walks"], w["walk_length"], w["p"], w["q"], seed=seed, out=out)
+
+    _, _, stats = g.walk(start, w["num_walks"], w["walk_length"], w["p"], w["q"], seed=seed, collect_stats=True)
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        one_pass()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        for a, b in ev:
+            flush.fill_(1)               # L2 flush between timed iterations (outside the events)
+            a.record()
+            one_pass()
+            b.record()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([float(sum(ms))], device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = world * steps_per_pass / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API, host buffers in, host walk matrix out
+    src_pin = torch.as_tensor(src).pin_memory()
+    dst_pin = torch.as_tensor(dst).pin_memory()
+    host_out = torch.empty((W, w["walk_length"] + 1), dtype=torch.int32).pin_memory()
+    params = {"num_walks": w["num_walks"], "walk_length": w["walk_length"], "return_param": w["p"],
+              "inout_param": w["q"]}
+
+    def e2e_pass():
+        res = fugue.random_walk(None, (src_pin, dst_pin), dict(params), random_seed=seed)
+        host_out.copy_(res.walks_device, non_blocking=True)
+        torch.cuda.synchronize()
+        return res
+
+    e2e_pass()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(2, min(args.steps, 5))
+    for _ in range(n_e2e):
+        e2e_pass()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * steps_per_pass / float(e2e_s.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    b_step, T, lp = walk_bytes_per_step(stats)
+    kernel_ms = float(np.mean(ms))
+    achieved = steps_per_pass * b_step / (kernel_ms * 1e-3) / 1e9
+    line = {
+        "metric": "walk_steps_per_s", "value": value, "unit": "walk-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": name, **{k: w[k] for k in ("graph", "p", "q", "num_walks", "walk_length")},
+                   "walkers_per_gpu": W, "arcs": int(g.n_arcs), "l2": "flushed between timed iterations (256 MiB write)",
+                   "sharding": "replicated CSR, walkers sharded by (start vertex, walk number); no collective"},
+        "gpu_launches": args.steps,
+        "e2e": {"value": e2e_value, "unit": "walk-steps/s",
+                "h2d_bytes_per_step": int(src_pin.numel() * 4 + dst_pin.numel() * 4),
+                "d2h_bytes_per_step": int(host_out.numel() * 4),
+                "what": "fugue.random_walk(host arcs) = H2D + csr_build + alias_build + walk, then D2H of the walk matrix"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "walk_kernel", "bytes_per_step": b_step,
+                     "trials_per_step": T, "probes_per_trial": lp, "kernel_ms": kernel_ms, "peak_source": peak_src,
+                     "note": "graph (10 MB) is L2-resident: effective-bandwidth figure, see profiles/"},
+        "clocks": clocks.summary(),
+        "walk_stats": stats,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_walk(name)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,194 @@
+/*
+ * n2v_b200.h -- C ABI of libn2v_b200.so: the B200 (sm_100a) replacement for the hot
+ * path of graph-embedding/node2vec 0.3.5 (node2vec-fugue).
+ *
+ * The reference is pure Python and has no FFI; the "interface each entry point
+ * replaces" is therefore the reference FUNCTION whose work it takes over, cited as
+ * file:line into the reference tree.  The Python host (node2vec_b200/) binds these
+ * with ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, PODs.  No torch / C++ types cross the boundary.
+ *   - every pointer is a DEVICE pointer unless the name ends in _host.
+ *   - the library owns no persistent memory: callers (torch tensors) own every buffer,
+ *     scratch included; sizes come from the *_scratch_bytes() queries.
+ *   - `stream` is a cudaStream_t passed as void* (torch's current stream); calls are
+ *     asynchronous on it and never synchronise unless documented.
+ *   - return value: 0 = OK, non-zero = error; n2v_last_error() gives the message for
+ *     the calling thread.  No exception crosses the ABI.
+ *   - re-entrant, no global state; one host thread per GPU/process is the intended use.
+ */
+#ifndef N2V_B200_H_
+#define N2V_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define N2V_ABI_VERSION 1
+#define N2V_MAX_PARTS 16
+
+/* error codes */
+enum {
+  N2V_OK = 0,
+  N2V_ERR_INVALID = 1,   /* bad argument (the Python host raises ValueError) */
+  N2V_ERR_CUDA = 2,      /* CUDA runtime error; message has the cudaError string */
+  N2V_ERR_SCRATCH = 3,   /* scratch buffer too small */
+  N2V_ERR_ZERO_WEIGHT = 4 /* a vertex's out-weights sum to 0 (reference: ZeroDivisionError, randomwalk.py:172-173) */
+};
+
+/* how `sum(node_weights)` (randomwalk.py:172) is evaluated -- see DESIGN.md "sum modes" */
+enum {
+  N2V_SUM_NAIVE = 0,     /* left-to-right fp64: CPython <= 3.11, the reference's supported 3.6/3.7 */
+  N2V_SUM_NEUMAIER = 1   /* CPython >= 3.12 builtin sum() float path */
+};
+
+/* graph property flags (set by n2v_csr_build, consumed by n2v_walk) */
+enum {
+  N2V_GRAPH_UNIT_WEIGHT = 1u,  /* every arc weight == 1.0 */
+  N2V_GRAPH_SYMMETRIC = 2u,    /* arc (a,b,w) present  <=>  arc (b,a,w) present */
+  N2V_GRAPH_SIMPLE = 4u        /* no repeated (src,dst) pair */
+};
+
+/* One vertex of the CSR: replaces one row of df_adj, i.e. one base64(pickle) adjacency
+ * string (randomwalk.py:266-275, Neighbors :17-41).  16 B, loaded as one LDG.128. */
+typedef struct n2v_vertex {
+  uint64_t base; /* index of the first out-arc in arcs[] / col[] / weight[] */
+  uint32_t deg;  /* number of out-arcs */
+  float wsum;    /* (float) of the fp64 left-to-right sum of out-weights; used only by the weighted return-edge fold */
+} n2v_vertex_t;
+
+/* One out-arc with its FIRST-ORDER alias-table entry folded in: replaces the
+ * (alias[k], probs[k]) pair of generate_alias_tables (randomwalk.py:157-190) plus the
+ * neighbour id, so that one alias draw is ONE 16-byte gather.
+ *   thr       = min(ceil(probs[k] * 2^32), 2^32 - 1): `u32 < thr`  <=>  `r2 < probs[k]`
+ *   dst       = neighbour id at index k          (taken when u32 <  thr)
+ *   alias_dst = neighbour id at index alias[k]   (taken when u32 >= thr); == dst when probs[k] >= 1
+ *   alias_idx = alias[k] exactly as the reference computes it */
+typedef struct n2v_arc {
+  uint32_t thr;
+  int32_t dst;
+  int32_t alias_dst;
+  int32_t alias_idx;
+} n2v_arc_t;
+
+/* One vertex-range shard of the CSR.  A replicated graph has exactly one part that
+ * covers [0, n_vertices).  With a vertex-partitioned CSR the pointers of remote parts
+ * are CUDA-IPC-mapped peer addresses (NVLink loads). */
+typedef struct n2v_graph_part {
+  const n2v_vertex_t* vtx;  /* [v_hi - v_lo], indexed by (v - v_lo); base is local to this part */
+  const n2v_arc_t* arcs;    /* [part arcs] */
+  const int32_t* col;       /* [part arcs] neighbour ids, ascending within a vertex */
+  const double* weight;     /* [part arcs] fp64 weights in col order */
+} n2v_graph_part_t;
+
+typedef struct n2v_graph {
+  int64_t n_vertices;   /* ids are 0 .. n_vertices-1; ids absent from the arc list have deg 0 */
+  int64_t n_arcs;       /* total over all parts */
+  uint32_t flags;       /* N2V_GRAPH_* */
+  int32_t n_parts;      /* 1 = replicated */
+  int64_t part_size;    /* vertices per part (last may be short); part(v) = v / part_size */
+  n2v_graph_part_t parts[N2V_MAX_PARTS];
+} n2v_graph_t;
+
+/* Counters returned by n2v_walk (device memory, 8 x uint64, accumulated with atomics;
+ * the caller zeroes them).  They feed the roofline's algorithmic-bytes formula. */
+typedef struct n2v_walk_stats {
+  uint64_t steps;        /* walker-steps taken */
+  uint64_t trials;       /* alias proposals drawn (>= steps; == steps when p == q == 1) */
+  uint64_t probes;       /* binary-search probes into N_out(prev) */
+  uint64_t searches;     /* membership tests that needed a search */
+  uint64_t fold_hits;    /* steps resolved by the return-edge fold without a proposal */
+  uint64_t fallbacks;    /* steps resolved by the exact O(deg) scan after N2V_MAX_TRIALS rejections */
+  uint64_t dead;         /* walkers dropped at a vertex with no out-arcs (fugue.py:147 inner join) */
+  uint64_t reserved;
+} n2v_walk_stats_t;
+
+/* ---- housekeeping ----------------------------------------------------------------- */
+int n2v_abi_version(void);
+const char* n2v_last_error(void);
+
+/* ---- K0: arcs -> sorted CSR -------------------------------------------------------
+ * Replaces `partition(by=["src"], presort="dst")` + get_vertex_neighbors
+ * (fugue.py:130, randomwalk.py:266-275).
+ * src/dst: [n_arcs] int32 ids in [0, n_vertices); weight: [n_arcs] fp64 or NULL (=1.0).
+ * Out: vtx[n_vertices] (base, deg; wsum filled by n2v_alias_build), col[n_arcs],
+ * weight_sorted[n_arcs], perm[n_arcs] (input position of each sorted arc; may be NULL),
+ * *flags_host (N2V_GRAPH_*; this call synchronises the stream to return it).
+ * Arcs are ordered by (src, dst); equal pairs keep input order (stable). */
+size_t n2v_csr_scratch_bytes(int64_t n_arcs, int64_t n_vertices);
+int n2v_csr_build(const int32_t* src, const int32_t* dst, const double* weight, int64_t n_arcs,
+                  int64_t n_vertices, n2v_vertex_t* vtx, int32_t* col, double* weight_sorted,
+                  int64_t* perm, void* scratch, size_t scratch_bytes, uint32_t* flags_host,
+                  void* stream);
+
+/* ---- K1: per-vertex first-order alias tables, bit-exact fp64 ------------------------
+ * Replaces generate_alias_tables (randomwalk.py:157-190) for every vertex at once (the
+ * reference re-runs it per walker per step, :320-321).
+ * Out: alias[n_arcs] int32 and probs[n_arcs] fp64 exactly as the reference returns them
+ * per vertex (either may be NULL), arcs[n_arcs] packed records, vtx[].wsum.
+ * scratch: n_arcs int32 (the two LIFO work-lists share each vertex's slice).
+ * *n_zero_host: number of vertices with deg > 0 whose weights sum to 0 (their tables are
+ * left zeroed; the host raises).  Synchronises the stream to return it. */
+int n2v_alias_build(n2v_vertex_t* vtx, const int32_t* col, const double* weight_sorted,
+                    int64_t n_vertices, int64_t n_arcs, int sum_mode, int32_t* alias,
+                    double* probs, n2v_arc_t* arcs, int32_t* scratch, int64_t* n_zero_host,
+                    void* stream);
+
+/* ---- a4: second-order (p,q) alias tables for explicit (prev, cur) pairs -------------
+ * Replaces generate_edge_alias_tables (randomwalk.py:193-232).  The walk kernel never
+ * materialises these (that is the point); this entry point exists so the bit-exact
+ * parity of the biasing + table construction can be shown on the device.
+ * prev/cur: [n_pairs]; prev < 0 means "first step" (unbiased, randomwalk.py:320-321).
+ * Table i is written at out_offset[i] .. out_offset[i] + deg(cur[i]) in alias_out /
+ * probs_out; scratch has the same layout (int32).  Single-part graphs only. */
+int n2v_edge_alias_build(const n2v_graph_t* graph, const int32_t* prev, const int32_t* cur,
+                         int64_t n_pairs, double return_param, double inout_param, int sum_mode,
+                         const int64_t* out_offset, int32_t* alias_out, double* probs_out,
+                         int32_t* scratch, void* stream);
+
+/* ---- a5/a6: the two alias samplers on explicit fp64 uniforms ------------------------
+ * Replaces AliasProb.sampling_from_alias (randomwalk.py:86-99; second != NULL) and
+ * sampling_from_alias_wiki (:70-84; second == NULL).  Table i is
+ * alias[offset[i] .. offset[i+1]).  Out: picked index per draw. */
+int n2v_alias_draw(const int32_t* alias, const double* probs, const int64_t* offset,
+                   const double* first, const double* second, int64_t n_draws, int32_t* picked,
+                   void* stream);
+
+/* ---- K2: second-order biased random walks ------------------------------------------
+ * Replaces initiate_random_walk + [two joins + next_step_random_walk] x walk_length +
+ * to_path (randomwalk.py:279-349, fugue.py:137-153).
+ * Walker w = s * num_walks + r  (s indexes start[], r = 0..num_walks-1) writes row w of
+ * walks[n_start*num_walks][pitch] (int32; pitch >= walk_length+1, pitch % 8 == 0):
+ * walk_length+1 vertex ids, entries past the end of a dropped walk are -1.
+ * alive[w] = 1 if the walker took all walk_length steps, 0 if it was dropped at a vertex
+ * without out-arcs (the reference's inner join drops the whole row, fugue.py:147).
+ * Randomness: Philox4x32-10, key = seed, counter = (walk_id lo, walk_id hi, step, trial)
+ * with walk_id = start[s] * num_walks + r, so results do not depend on sharding.
+ * stats: device n2v_walk_stats_t, accumulated (caller zeroes); may be NULL. */
+int n2v_walk(const n2v_graph_t* graph, const int32_t* start, int64_t n_start, int32_t num_walks,
+             int32_t walk_length, double return_param, double inout_param, uint64_t seed,
+             int32_t* walks, int64_t pitch, uint8_t* alive, n2v_walk_stats_t* stats,
+             void* stream);
+
+/* The sampling constants n2v_walk derives from (p, q, graph flags); exposed so the host
+ * replay in oracle/ and the roofline calculator use exactly the same numbers. */
+typedef struct n2v_walk_consts {
+  uint64_t t_ret;   /* accept x == prev      iff u32 < t_ret   (values in [0, 2^32]) */
+  uint64_t t_nbr;   /* accept x in N_out(prev) iff u32 < t_nbr */
+  uint64_t t_far;   /* accept otherwise      iff u32 < t_far */
+  float fold_gain;  /* e' = max(0, 1/p - cap) / cap; 0 = return-edge fold off */
+  int32_t fold_mode;/* 0 off, 1 unit-weight symmetric simple graph (rho = 1/deg), 2 general */
+  int32_t max_trials;
+  int32_t reserved;
+} n2v_walk_consts_t;
+int n2v_walk_consts(double return_param, double inout_param, uint32_t graph_flags,
+                    n2v_walk_consts_t* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* N2V_B200_H_ */

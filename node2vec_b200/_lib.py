@@ -1,0 +1,116 @@
+"""ctypes binding of libn2v_b200.so (the C ABI in include/n2v_b200.h).
+
+The library is the product: if it is missing or a call fails this module raises -- there
+is no fallback path of any kind.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+N2V_MAX_PARTS = 16
+OK, ERR_INVALID, ERR_CUDA, ERR_SCRATCH, ERR_ZERO_WEIGHT = 0, 1, 2, 3, 4
+SUM_MODE = {"naive": 0, "neumaier": 1}
+GRAPH_UNIT_WEIGHT, GRAPH_SYMMETRIC, GRAPH_SIMPLE = 1, 2, 4
+
+
+class GraphPart(C.Structure):
+    _fields_ = [("vtx", C.c_void_p), ("arcs", C.c_void_p), ("col", C.c_void_p), ("weight", C.c_void_p)]
+
+
+class Graph(C.Structure):
+    _fields_ = [("n_vertices", C.c_int64), ("n_arcs", C.c_int64), ("flags", C.c_uint32),
+                ("n_parts", C.c_int32), ("part_size", C.c_int64), ("parts", GraphPart * N2V_MAX_PARTS)]
+
+
+class WalkConsts(C.Structure):
+    _fields_ = [("t_ret", C.c_uint64), ("t_nbr", C.c_uint64), ("t_far", C.c_uint64),
+                ("fold_gain", C.c_float), ("fold_mode", C.c_int32), ("max_trials", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+WALK_STAT_NAMES = ("steps", "trials", "probes", "searches", "fold_hits", "fallbacks", "dead", "reserved")
+
+_P = C.c_void_p
+_SIGNATURES = {
+    "n2v_abi_version": (C.c_int, []),
+    "n2v_last_error": (C.c_char_p, []),
+    "n2v_csr_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "n2v_csr_build": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t,
+                                C.POINTER(C.c_uint32), _P]),
+    "n2v_alias_build": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P, _P, _P,
+                                  C.POINTER(C.c_int64), _P]),
+    "n2v_edge_alias_build": (C.c_int, [C.POINTER(Graph), _P, _P, C.c_int64, C.c_double, C.c_double, C.c_int,
+                                       _P, _P, _P, _P, _P]),
+    "n2v_alias_draw": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P]),
+    "n2v_walk": (C.c_int, [C.POINTER(Graph), _P, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double,
+                           C.c_uint64, _P, C.c_int64, _P, _P, _P]),
+    "n2v_walk_consts": (C.c_int, [C.c_double, C.c_double, C.c_uint32, C.POINTER(WalkConsts)]),
+}
+
+_lib = None
+
+
+class N2VError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _build.SO
+
+
+def load(build_if_missing: bool = True):
+    """Load libn2v_b200.so, building it with nvcc when absent.  Raises if it cannot."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_build.SO):
+        if not build_if_missing:
+            raise N2VError(f"{_build.SO} is missing: run `python -m node2vec_b200.build`")
+        _build.build_library()
+    lib = C.CDLL(_build.SO)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = ABI mismatch, loudly
+        fn.restype = res
+        fn.argtypes = args
+    for name, (res, args) in _optional_signatures().items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _optional_signatures():
+    try:
+        from ._lib_sgns import SIGNATURES
+        return SIGNATURES
+    except ImportError:
+        return {}
+
+
+def check(rc: int, what: str = ""):
+    """Map a status code to the exception the reference's callers expect."""
+    if rc == OK:
+        return
+    msg = load().n2v_last_error().decode("utf-8", "replace")
+    if rc in (ERR_INVALID, ERR_ZERO_WEIGHT):
+        raise ValueError(msg)
+    raise N2VError(f"{what}: {msg} (code {rc})")
+
+
+def current_stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise N2VError("node2vec_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / None."""
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())

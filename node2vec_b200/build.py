@@ -1,0 +1,44 @@
+"""Compile node2vec_b200/csrc/*.cu into libn2v_b200.so for sm_100a (nvcc, in-tree)."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(CSRC, "libn2v_b200.so")
+SOURCES = ["abi.cu", "csr_build.cu", "alias_build.cu", "walk.cu", "vocab.cu", "sgns.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--extended-lambda", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+]
+
+
+def sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def is_stale() -> bool:
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = sources() + [os.path.join(CSRC, "n2v_internal.cuh"),
+                        os.path.join(HERE, "..", "include", "n2v_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build_library(force: bool = False, extra_flags=(), verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return SO
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libn2v_b200.so")
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-o", SO] + sources()
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd, cwd=CSRC)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,80 @@
+// Internal helpers shared by the .cu files of libn2v_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/n2v_b200.h"
+
+namespace n2v {
+
+void set_error(const char* fmt, ...);
+
+#define N2V_CHECK_ARG(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      n2v::set_error(__VA_ARGS__);          \
+      return N2V_ERR_INVALID;               \
+    }                                       \
+  } while (0)
+
+#define N2V_CUDA(call)                                                                    \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      n2v::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return N2V_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+// launch-error check that does not synchronise
+#define N2V_LAUNCH_OK() N2V_CUDA(cudaGetLastError())
+
+constexpr int kSmCount = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// ---- 16-byte record loads (one LDG.128 each, read-only path) ------------------------
+struct VtxRec {
+  uint64_t base;
+  uint32_t deg;
+  float wsum;
+};
+
+__device__ __forceinline__ VtxRec load_vtx(const n2v_vertex_t* p) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  VtxRec r;
+  r.base = (static_cast<uint64_t>(q.y) << 32) | q.x;
+  r.deg = q.z;
+  r.wsum = __uint_as_float(q.w);
+  return r;
+}
+
+__device__ __forceinline__ int4 load_arc(const n2v_arc_t* p) {
+  return __ldg(reinterpret_cast<const int4*>(p));
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11), counter-based ------------------------------
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0,
+                                                        uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+}  // namespace n2v

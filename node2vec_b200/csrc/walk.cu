@@ -1,0 +1,326 @@
+// K2: second-order (p, q) biased random walks over the packed CSR.
+//
+// Replaces, for every walker at once, the reference's
+//   initiate_random_walk                      (randomwalk.py:279-296)
+//   [left join on src, inner join on dst]     (fugue.py:147)
+//   next_step_random_walk  x walk_length      (randomwalk.py:300-339), which per row
+//       unpickles two adjacency strings, rebuilds an O(deg) alias table
+//       (generate_edge_alias_tables :193-232) and draws once (:86-99)
+//   to_path                                   (randomwalk.py:343-349)
+//
+// Sampling.  The reference's law for the next vertex x, given the previous vertex t and
+// the current vertex v, is  P(x) ~ w(v,x) * alpha(t,x)  with alpha = 1/p (x == t),
+// 1 (x in N_out(t)), 1/q (otherwise) (randomwalk.py:223-230).  We draw from exactly that
+// law without building the per-(t,v) table: propose x from v's FIRST-ORDER alias table
+// (one 16-byte gather), accept with alpha/cap; membership in N_out(t) is a binary search
+// of t's sorted neighbour slice and is skipped whenever the accept draw already decides
+// (u below both thresholds / above both).  The return arc's excess mass (1/p above cap)
+// is a separate mixture component (the "fold"), so small p does not inflate the envelope.
+//
+// Execution model.  One thread per walker, lanes fully asynchronous: the loop body is ONE
+// proposal; a lane whose proposal is accepted advances its own step counter, a lane that
+// finishes its walk picks up the next walker (grid-stride).  Nobody waits for a
+// neighbour's rejections.  Walk rows are staged 8 ids at a time per lane and written as
+// whole 32-byte sectors.
+//
+// Determinism.  Philox4x32-10, key = seed, counter = (walk_id lo, walk_id hi, step,
+// trial); all sampling decisions are integer compares, the fold threshold is three IEEE
+// fp32 ops.  oracle/csrc/walk_replay.c restates this on the host bit-for-bit.
+#include "n2v_internal.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+#ifndef N2V_WALK_BLOCKS_PER_SM
+#define N2V_WALK_BLOCKS_PER_SM 8
+#endif
+constexpr int kBlocksPerSm = N2V_WALK_BLOCKS_PER_SM;
+constexpr int kStage = 8;  // ids per lane per flush = one 32 B sector
+
+struct WalkArgs {
+  const int32_t* start;
+  int64_t n_start;
+  int64_t n_walkers;
+  int32_t num_walks;
+  int32_t walk_length;
+  uint32_t key0, key1;
+  int32_t* walks;
+  int64_t pitch;
+  uint8_t* alive;
+  unsigned long long* stats;
+  // accept iff u32 <= *_m1
+  uint32_t ret_m1, nbr_m1, far_m1, lo_m1, hi_m1;
+  float fold_gain;
+  int32_t max_trials;
+  double inv_p, inv_q;
+};
+
+struct Part {
+  const n2v_vertex_t* vtx;
+  const n2v_arc_t* arcs;
+  const int32_t* col;
+  const double* weight;
+};
+
+template <bool MULTI>
+__device__ __forceinline__ Part part_of(const n2v_graph_t& g, int32_t v, int32_t& local) {
+  if (MULTI) {
+    const int32_t pi = static_cast<int32_t>(v / g.part_size);
+    local = v - static_cast<int32_t>(pi * g.part_size);
+    const n2v_graph_part_t& p = g.parts[pi];
+    return Part{p.vtx, p.arcs, p.col, p.weight};
+  }
+  local = v;
+  const n2v_graph_part_t& p = g.parts[0];
+  return Part{p.vtx, p.arcs, p.col, p.weight};
+}
+
+// lower_bound membership test in an ascending slice; counts probes
+__device__ __forceinline__ bool member(const int32_t* __restrict__ col, uint32_t n, int32_t x,
+                                       uint32_t& probes) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    ++probes;
+    if (__ldg(col + mid) < x) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= n) return false;
+  ++probes;
+  return __ldg(col + lo) == x;
+}
+
+// Exact O(deg log deg) draw from the biased law; used only after max_trials rejections so
+// that extreme (p, q) on a hub cannot stall a lane.  Sequential fp64, no contraction.
+__device__ __noinline__ int32_t exact_draw(const int32_t* __restrict__ vcol, const double* __restrict__ vw,
+                                           uint32_t deg, int32_t t, const int32_t* __restrict__ tcol,
+                                           uint32_t tdeg, double inv_p, double inv_q, uint32_t r0,
+                                           uint32_t r1, uint32_t& probes) {
+  double total = 0.0;
+  for (uint32_t i = 0; i < deg; ++i) {
+    const int32_t x = vcol[i];
+    const double a = (x == t) ? inv_p : (member(tcol, tdeg, x, probes) ? 1.0 : inv_q);
+    total = __dadd_rn(total, __dmul_rn(vw[i], a));
+  }
+  // 53-bit uniform in [0,1) from two 32-bit lanes
+  const double u = __dmul_rn(__dadd_rn(__dmul_rn(static_cast<double>(r0 >> 5), 67108864.0),
+                                       static_cast<double>(r1 >> 6)),
+                             1.0 / 9007199254740992.0);
+  const double target = __dmul_rn(u, total);
+  double run = 0.0;
+  int32_t last = vcol[deg - 1];
+  for (uint32_t i = 0; i < deg; ++i) {
+    const int32_t x = vcol[i];
+    const double a = (x == t) ? inv_p : (member(tcol, tdeg, x, probes) ? 1.0 : inv_q);
+    const double m = __dmul_rn(vw[i], a);
+    run = __dadd_rn(run, m);
+    if (m > 0.0) last = x;
+    if (target < run) return x;
+  }
+  return last;
+}
+
+__device__ __forceinline__ uint32_t fold_threshold(float gain, uint32_t deg) {
+  // P(return via fold) = gain / (deg + gain) on a unit-weight symmetric simple graph
+  const float pr = __fdiv_rn(gain, __fadd_rn(static_cast<float>(deg), gain));
+  return pr >= 1.0f ? 0xFFFFFFFFu : __float2uint_rz(__fmul_rn(pr, 4294967296.0f));
+}
+
+template <bool FOLD, bool MULTI, bool STATS>
+__global__ void __launch_bounds__(kBlock, kBlocksPerSm)
+walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkArgs A) {
+  __shared__ int32_t stage[kStage * kBlock];  // [slot][thread]: conflict-free
+  const int tid = threadIdx.x;
+  const int64_t stride = int64_t(gridDim.x) * kBlock;
+  int64_t w = blockIdx.x * int64_t(kBlock) + tid;
+
+  uint32_t c_steps = 0, c_trials = 0, c_probes = 0, c_search = 0, c_fold = 0, c_fb = 0, c_dead = 0;
+
+  // walker state
+  int32_t t = -1, v = 0, pos = 0;
+  uint32_t deg_t = 0, deg_v = 0, trial = 0, thr_out = 0;
+  uint64_t base_v = 0, walk_id = 0;
+  Part pv{};
+  const int32_t* tcol = nullptr;
+  bool active = false;
+  const int32_t L = A.walk_length;
+
+  auto flush_chunk = [&](int chunk) {
+    int4 a, b;
+    a.x = stage[0 * kBlock + tid]; a.y = stage[1 * kBlock + tid];
+    a.z = stage[2 * kBlock + tid]; a.w = stage[3 * kBlock + tid];
+    b.x = stage[4 * kBlock + tid]; b.y = stage[5 * kBlock + tid];
+    b.z = stage[6 * kBlock + tid]; b.w = stage[7 * kBlock + tid];
+    int4* dst = reinterpret_cast<int4*>(A.walks + w * A.pitch + int64_t(chunk) * kStage);
+    dst[0] = a;
+    dst[1] = b;
+  };
+  // end of a walk (complete or dropped): pad the row with -1 and release the lane
+  auto finish = [&](bool is_alive) {
+    for (int s = (pos & (kStage - 1)) + 1; s < kStage; ++s) stage[s * kBlock + tid] = -1;
+    int chunk = pos >> 3;
+    flush_chunk(chunk);
+    const int4 neg = make_int4(-1, -1, -1, -1);
+    for (++chunk; chunk * kStage < A.pitch; ++chunk) {
+      int4* dst = reinterpret_cast<int4*>(A.walks + w * A.pitch + int64_t(chunk) * kStage);
+      dst[0] = neg;
+      dst[1] = neg;
+    }
+    A.alive[w] = is_alive ? 1 : 0;
+    active = false;
+    w += stride;
+  };
+
+  for (;;) {
+    if (!active) {
+      if (w >= A.n_walkers) break;
+      const int64_t s = w / A.num_walks;
+      const int32_t r = static_cast<int32_t>(w - s * A.num_walks);
+      v = __ldg(A.start + s);
+      walk_id = static_cast<uint64_t>(static_cast<uint32_t>(v)) * static_cast<uint32_t>(A.num_walks) + r;
+      int32_t local;
+      pv = part_of<MULTI>(g, v, local);
+      const n2v::VtxRec rec = n2v::load_vtx(pv.vtx + local);
+      base_v = rec.base;
+      deg_v = rec.deg;
+      t = -1;
+      pos = 0;
+      trial = 0;
+      stage[tid] = v;
+      active = true;
+    }
+    if (deg_v == 0) {  // inner join with df_dst drops the row (fugue.py:147)
+      if (STATS) ++c_dead;
+      finish(false);
+      continue;
+    }
+    const uint4 rnd = n2v::philox4x32_10(A.key0, A.key1, static_cast<uint32_t>(walk_id),
+                                         static_cast<uint32_t>(walk_id >> 32),
+                                         static_cast<uint32_t>(pos), trial);
+    const bool first = (pos == 0);
+    bool accept;
+    int32_t x;
+    if (FOLD && !first && rnd.x < thr_out) {
+      x = t;
+      accept = true;
+      if (STATS) ++c_fold;
+    } else {
+      const uint32_t k = __umulhi(rnd.y, deg_v);
+      const int4 arc = n2v::load_arc(pv.arcs + base_v + k);
+      x = (rnd.z < static_cast<uint32_t>(arc.x)) ? arc.y : arc.z;
+      if (STATS) ++c_trials;
+      if (first) accept = true;                       // unbiased first step (randomwalk.py:320-321)
+      else if (x == t) accept = rnd.w <= A.ret_m1;
+      else if (rnd.w <= A.lo_m1) accept = true;       // below both thresholds: no search needed
+      else if (rnd.w > A.hi_m1) accept = false;       // above both
+      else {
+        if (STATS) ++c_search;
+        accept = rnd.w <= (member(tcol, deg_t, x, c_probes) ? A.nbr_m1 : A.far_m1);
+      }
+    }
+    if (!accept) {
+      if (++trial < static_cast<uint32_t>(A.max_trials)) continue;
+      const uint4 r2 = n2v::philox4x32_10(A.key0, A.key1, static_cast<uint32_t>(walk_id),
+                                          static_cast<uint32_t>(walk_id >> 32),
+                                          static_cast<uint32_t>(pos), 0xFFFFFFFFu);
+      x = exact_draw(pv.col + base_v, pv.weight + base_v, deg_v, t, tcol, deg_t, A.inv_p, A.inv_q,
+                     r2.x, r2.y, c_probes);
+      if (STATS) ++c_fb;
+    }
+    // advance: v becomes the previous vertex
+    t = v;
+    tcol = pv.col + base_v;
+    deg_t = deg_v;
+    v = x;
+    int32_t local;
+    pv = part_of<MULTI>(g, v, local);
+    const n2v::VtxRec rec = n2v::load_vtx(pv.vtx + local);
+    base_v = rec.base;
+    deg_v = rec.deg;
+    ++pos;
+    if (STATS) ++c_steps;
+    trial = 0;
+    stage[(pos & (kStage - 1)) * kBlock + tid] = v;
+    if (pos == L) {
+      finish(true);
+      continue;
+    }
+    if ((pos & (kStage - 1)) == kStage - 1) flush_chunk(pos >> 3);
+    if (FOLD) thr_out = fold_threshold(A.fold_gain, deg_v);
+  }
+
+  // one atomic per counter per warp
+  unsigned long long vals[7] = {c_steps, c_trials, c_probes, c_search, c_fold, c_fb, c_dead};
+  if (STATS) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      unsigned long long x = vals[i];
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if ((tid & 31) == 0 && x) atomicAdd(A.stats + i, x);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int n2v_walk(const n2v_graph_t* graph, const int32_t* start, int64_t n_start,
+                        int32_t num_walks, int32_t walk_length, double return_param,
+                        double inout_param, uint64_t seed, int32_t* walks, int64_t pitch,
+                        uint8_t* alive, n2v_walk_stats_t* stats, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  N2V_CHECK_ARG(graph != nullptr, "n2v_walk: graph is NULL");
+  N2V_CHECK_ARG(graph->n_parts >= 1 && graph->n_parts <= N2V_MAX_PARTS, "n2v_walk: n_parts %d out of range", graph->n_parts);
+  N2V_CHECK_ARG(num_walks >= 1 && walk_length >= 1, "n2v_walk: num_walks (%d) and walk_length (%d) must be >= 1",
+                num_walks, walk_length);
+  N2V_CHECK_ARG(pitch >= walk_length + 1 && pitch % kStage == 0,
+                "n2v_walk: pitch %lld must be a multiple of 8 and >= walk_length+1", static_cast<long long>(pitch));
+  N2V_CHECK_ARG(n_start >= 0, "n2v_walk: negative n_start");
+  n2v_walk_consts_t C;
+  const int rc = n2v_walk_consts(return_param, inout_param, graph->flags, &C);
+  if (rc != N2V_OK) return rc;
+  if (n_start == 0) return N2V_OK;
+  N2V_CHECK_ARG(start && walks && alive, "n2v_walk: NULL buffer");
+  N2V_CHECK_ARG((reinterpret_cast<uintptr_t>(walks) & 31) == 0, "n2v_walk: walks must be 32-byte aligned");
+
+  WalkArgs A{};
+  A.start = start;
+  A.n_start = n_start;
+  A.n_walkers = n_start * num_walks;
+  A.num_walks = num_walks;
+  A.walk_length = walk_length;
+  A.key0 = static_cast<uint32_t>(seed);
+  A.key1 = static_cast<uint32_t>(seed >> 32);
+  A.walks = walks;
+  A.pitch = pitch;
+  A.alive = alive;
+  A.stats = reinterpret_cast<unsigned long long*>(stats);
+  A.ret_m1 = static_cast<uint32_t>(C.t_ret - 1);
+  A.nbr_m1 = static_cast<uint32_t>(C.t_nbr - 1);
+  A.far_m1 = static_cast<uint32_t>(C.t_far - 1);
+  A.lo_m1 = A.nbr_m1 < A.far_m1 ? A.nbr_m1 : A.far_m1;
+  A.hi_m1 = A.nbr_m1 < A.far_m1 ? A.far_m1 : A.nbr_m1;
+  A.fold_gain = C.fold_gain;
+  A.max_trials = C.max_trials;
+  A.inv_p = 1.0 / return_param;
+  A.inv_q = 1.0 / inout_param;
+
+  const int64_t need = (A.n_walkers + kBlock - 1) / kBlock;
+  const int64_t cap = int64_t(n2v::kSmCount) * kBlocksPerSm;
+  const int grid = static_cast<int>(need < cap ? need : cap);
+  const bool fold = C.fold_mode != 0;
+  const bool multi = graph->n_parts > 1;
+  const bool st = stats != nullptr;
+#define N2V_LAUNCH_WALK(F, M, S) walk_kernel<F, M, S><<<grid, kBlock, 0, stream>>>(*graph, A)
+  switch ((fold ? 4 : 0) | (multi ? 2 : 0) | (st ? 1 : 0)) {
+    case 0: N2V_LAUNCH_WALK(false, false, false); break;
+    case 1: N2V_LAUNCH_WALK(false, false, true); break;
+    case 2: N2V_LAUNCH_WALK(false, true, false); break;
+    case 3: N2V_LAUNCH_WALK(false, true, true); break;
+    case 4: N2V_LAUNCH_WALK(true, false, false); break;
+    case 5: N2V_LAUNCH_WALK(true, false, true); break;
+    case 6: N2V_LAUNCH_WALK(true, true, false); break;
+    default: N2V_LAUNCH_WALK(true, true, true); break;
+  }
+#undef N2V_LAUNCH_WALK
+  N2V_LAUNCH_OK();
+  return N2V_OK;
+}

@@ -1,0 +1,213 @@
+"""Drop-in for the reference's ``node2vec/fugue.py``: same two entry points, same
+arguments, same errors -- the body is the B200 engine instead of a Fugue DAG.
+
+``compute_engine`` is accepted for signature compatibility and ignored (Fugue is not a
+dependency; a Spark engine is rejected because its data lives in a JVM).  Frames are
+duck-typed: a pandas DataFrame, anything exposing ``.as_pandas()`` (Fugue
+``ArrayDataFrame`` / ``PandasDataFrame``), or -- for graphs too big for pandas -- a tuple
+of torch tensors / numpy arrays ``(src, dst[, weight])``.
+"""
+import logging
+from typing import Any, Dict, Optional, Tuple
+
+import numpy as np
+import pandas as pd
+import torch
+
+from .constants import MAX_OUT_DEGREES, NODE2VEC_PARAMS
+from .graph import DeviceGraph
+from .indexer import index_graph_pandas
+
+
+class Frame(object):
+    """Minimal stand-in for a Fugue DataFrame around a pandas frame."""
+
+    def __init__(self, df: pd.DataFrame):
+        self._df = df
+
+    @property
+    def native(self) -> pd.DataFrame:
+        return self._df
+
+    def as_pandas(self) -> pd.DataFrame:
+        return self._df
+
+    def as_array(self):
+        return self._df.values.tolist()
+
+    def count(self) -> int:
+        return len(self._df)
+
+    @property
+    def schema(self):
+        return list(self._df.columns)
+
+    def __len__(self):
+        return len(self._df)
+
+
+class WalkFrame(Frame):
+    """Result of ``random_walk``: the ``[src, walk]`` frame of the reference
+    (fugue.py:109-117), materialised lazily from the walk matrix.
+
+    ``walks``       int32 [W_alive, L+1] numpy matrix (host)
+    ``walks_device`` the same rows as a torch tensor still in HBM (for SGNS)
+    """
+
+    def __init__(self, walks_device: torch.Tensor, walks_host: Optional[np.ndarray] = None, stats=None):
+        self.walks_device = walks_device
+        self._host = walks_host
+        self.stats = stats
+        self._df = None
+
+    @property
+    def walks(self) -> np.ndarray:
+        if self._host is None:
+            self._host = self.walks_device.cpu().numpy()
+        return self._host
+
+    def as_pandas(self) -> pd.DataFrame:
+        if self._df is None:
+            w = self.walks
+            self._df = pd.DataFrame({"src": w[:, 0].astype(np.int64) if len(w) else np.zeros(0, dtype=np.int64),
+                                     "walk": w.tolist()})
+        return self._df
+
+    native = property(as_pandas)
+
+    def as_array(self):
+        return self.as_pandas().values.tolist()
+
+    def count(self) -> int:
+        return int(self.walks_device.shape[0])
+
+    @property
+    def schema(self):
+        return ["src", "walk"]
+
+    def __len__(self):
+        return self.count()
+
+
+def _columns(df) -> list:
+    if isinstance(df, pd.DataFrame):
+        return list(df.columns)
+    schema = getattr(df, "schema", None)
+    if schema is None:
+        raise ValueError(f"Unsupported frame type {type(df)}")
+    names = getattr(schema, "names", None)
+    return list(names) if names is not None else list(schema)
+
+
+def _to_pandas(df) -> pd.DataFrame:
+    if isinstance(df, pd.DataFrame):
+        return df
+    if hasattr(df, "as_pandas"):
+        return df.as_pandas()
+    raise ValueError(f"Unsupported frame type {type(df)}")
+
+
+def _reject_spark(engine) -> None:
+    if engine is not None and "spark" in type(engine).__name__.lower():
+        raise NotImplementedError("SparkExecutionEngine is out of scope: pass a pandas / Fugue-native frame")
+
+
+def trim_index(
+    compute_engine: Any,
+    df_graph: Any,
+    indexed: bool = False,
+    directed: bool = True,
+    max_out_deg: int = 0,
+    random_seed: Optional[int] = None,
+) -> Tuple[Frame, Optional[Frame]]:
+    """Validate, trim hotspot vertices, index.  Same contract as the reference
+    (fugue.py:24-77): ``max_out_deg <= 0`` means 100000 (randomwalk.py:254-255);
+    ``indexed=True`` returns the trimmed frame untouched and ``None``."""
+    logging.info("trim_index(): start validating, trimming, and indexing ...")
+    cols = _columns(df_graph)
+    if "src" not in cols or "dst" not in cols:
+        raise ValueError(f"Input graph NOT in the right format: {cols}")
+    _reject_spark(compute_engine)
+    df = _to_pandas(df_graph)
+    cap = max_out_deg if max_out_deg > 0 else MAX_OUT_DEGREES
+    # partition(by=["src"]) + trim_hotspot_vertices: groups come out in key order, rows in
+    # input order, an oversize group is replaced by DataFrame.sample(n=cap, random_state=seed)
+    df = df.sort_values("src", kind="stable")
+    sizes = df.groupby("src", sort=False)["src"].transform("size")
+    if (sizes > cap).any():
+        parts = []
+        for _, part in df.groupby("src", sort=True):
+            if len(part) > cap:
+                part = part.sample(n=cap, random_state=random_seed) if random_seed is not None \
+                    else part.sample(n=cap)
+            parts.append(part)
+        df = pd.concat(parts)
+    df = df.reset_index(drop=True)
+    if indexed is True:
+        return Frame(df), None
+    df_res, name_id = index_graph_pandas(df, directed)
+    return Frame(df_res.reset_index(drop=True)), Frame(name_id)
+
+
+def _graph_arrays(df_graph):
+    if isinstance(df_graph, (tuple, list)) and len(df_graph) in (2, 3) and not isinstance(df_graph[0], (int, float)):
+        src, dst = df_graph[0], df_graph[1]
+        weight = df_graph[2] if len(df_graph) == 3 else None
+        return src, dst, weight
+    cols = _columns(df_graph)
+    if "src" not in cols or "dst" not in cols:
+        raise ValueError(f"Input graph NOT in the right format: {cols}")
+    df = _to_pandas(df_graph)
+    weight = df["weight"].to_numpy(dtype=np.float64) if "weight" in df.columns else None
+    return df["src"].to_numpy(), df["dst"].to_numpy(), weight
+
+
+def random_walk(
+    compute_engine: Any,
+    df_graph: Any,
+    n2v_params: Dict[str, Any],
+    walk_seed: Any = None,
+    random_seed: Optional[int] = None,
+    checkpoint_dir: Optional[str] = "/tmp",
+    *,
+    graph: Optional[DeviceGraph] = None,
+    collect_stats: bool = False,
+) -> WalkFrame:
+    """Second-order biased random walks; same contract as the reference (fugue.py:81-155).
+
+    * defaults are merged into ``n2v_params`` in place (:120-122)
+    * ``walk_seed`` must have an ``id`` column, else ValueError (:123-124)
+    * only vertices with an out-arc start walks (:132), ``num_walks`` each, optionally
+      restricted to ``walk_seed`` ids (:133-134)
+    * a walker that reaches a vertex with no out-arcs before its last step is dropped (:147)
+    * returns ``[src, walk]`` with ``walk_length + 1`` vertices per walk (:153)
+    ``random_seed`` keys the Philox stream (None = fresh entropy).  ``checkpoint_dir`` is
+    accepted and unused: the walk matrix lives in HBM, there is no lineage to truncate.
+    Keyword-only extras: ``graph`` reuses a prebuilt DeviceGraph; ``collect_stats``.
+    """
+    logging.info("random_walk(): start random walking ...")
+    for param in NODE2VEC_PARAMS:
+        if param not in n2v_params:
+            n2v_params[param] = NODE2VEC_PARAMS[param]
+    if walk_seed is not None and "id" not in _columns(walk_seed):
+        raise ValueError(f"walk_seed has no column of 'id': {_columns(walk_seed)}!")
+    _reject_spark(compute_engine)
+    p, q = n2v_params["return_param"], n2v_params["inout_param"]
+    if p == 0 or q == 0:
+        raise ValueError(f"Zero return ({p}) or inout ({q}) parameter!")
+    num_walks, walk_length = int(n2v_params["num_walks"]), int(n2v_params["walk_length"])
+    if num_walks < 1 or walk_length < 1:
+        raise ValueError("num_walks and walk_length must be >= 1")
+
+    if graph is None:
+        src, dst, weight = _graph_arrays(df_graph)
+        graph = DeviceGraph.from_arcs(src, dst, weight)
+    start = graph.start_vertices()
+    if walk_seed is not None:
+        ids = torch.as_tensor(np.unique(_to_pandas(walk_seed)["id"].to_numpy().astype(np.int64)),
+                              device=start.device)
+        start = start[torch.isin(start.to(torch.int64), ids)]
+    walks, alive, stats = graph.walk(start, num_walks, walk_length, p, q, random_seed, collect_stats)
+    walks = walks[alive] if not bool(alive.all()) else walks
+    logging.info("random_walk(): random walking done ...")
+    return WalkFrame(walks, stats=stats)

@@ -1,0 +1,186 @@
+"""Device-resident graph + the walk launcher: the host side of K0/K1/K2.
+
+``DeviceGraph`` replaces the reference's ``df_adj`` frame of pickled adjacency strings
+(fugue.py:130, randomwalk.py:266-275): a packed CSR in HBM with every vertex's
+first-order alias table folded into its arc records (include/n2v_b200.h).
+PyTorch tensors own all device memory; kernels run on torch's current stream.
+"""
+import ctypes as C
+import os
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _as_device_i32(x, device) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.int32).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x).astype(np.int32, copy=False), device=device)
+
+
+def _as_device_f64(x, device) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float64).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x).astype(np.float64, copy=False), device=device)
+
+
+class DeviceGraph:
+    """Sorted CSR + alias records in HBM.
+
+    Layout (one replica):
+      vtx   int32[V, 4]   16 B/vertex  {base u64, deg u32, wsum f32}
+      arcs  int32[A, 4]   16 B/arc     {thr u32, dst i32, alias_dst i32, alias_idx i32}
+      col   int32[A]       4 B/arc     neighbour ids, ascending per vertex (membership search)
+      weight f64[A]        8 B/arc     reference weights (exact fallback, parity outputs)
+    ``alias`` / ``probs`` (the reference's tables, bit-exact) are kept only on request.
+    """
+
+    def __init__(self):
+        self.n_vertices = 0
+        self.n_arcs = 0
+        self.flags = 0
+        self.vtx = self.arcs = self.col = self.weight = None
+        self.alias = self.probs = self.perm = None
+        self.device = None
+        self.sum_mode = "naive"
+        self._struct = None
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_arcs(cls, src, dst, weight=None, n_vertices: Optional[int] = None, device=None,
+                  sum_mode: str = "naive", keep_tables: bool = False, keep_perm: bool = False) -> "DeviceGraph":
+        """K0 + K1.  src/dst: int ids (tensor or array); weight: fp64 or None (=1.0)."""
+        _lib.require_cuda()
+        lib = _lib.load()
+        if sum_mode not in _lib.SUM_MODE:
+            raise ValueError(f"unknown sum_mode {sum_mode!r}")
+        device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        g = cls()
+        g.device, g.sum_mode = device, sum_mode
+        with torch.cuda.device(device):
+            s = _as_device_i32(src, device)
+            d = _as_device_i32(dst, device)
+            w = None if weight is None else _as_device_f64(weight, device)
+            if s.numel() != d.numel() or (w is not None and w.numel() != s.numel()):
+                raise ValueError("src, dst and weight must have the same length")
+            n_arcs = int(s.numel())
+            if n_vertices is None:
+                n_vertices = int(max(int(s.max()), int(d.max())) + 1) if n_arcs else 0
+            g.n_vertices, g.n_arcs = int(n_vertices), n_arcs
+            stream = _lib.current_stream_ptr()
+            g.vtx = torch.empty((g.n_vertices, 4), dtype=torch.int32, device=device)
+            g.col = torch.empty(n_arcs, dtype=torch.int32, device=device)
+            g.weight = torch.empty(n_arcs, dtype=torch.float64, device=device)
+            if keep_perm:
+                g.perm = torch.empty(n_arcs, dtype=torch.int64, device=device)
+            nbytes = int(lib.n2v_csr_scratch_bytes(n_arcs, g.n_vertices))
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            flags = C.c_uint32(0)
+            _lib.check(lib.n2v_csr_build(_lib.ptr(s), _lib.ptr(d), _lib.ptr(w), n_arcs, g.n_vertices,
+                                         _lib.ptr(g.vtx), _lib.ptr(g.col), _lib.ptr(g.weight), _lib.ptr(g.perm),
+                                         _lib.ptr(scratch), nbytes, C.byref(flags), stream), "n2v_csr_build")
+            g.flags = int(flags.value)
+            del scratch, s, d, w
+            g.arcs = torch.empty((n_arcs, 4), dtype=torch.int32, device=device)
+            probs = torch.empty(n_arcs, dtype=torch.float64, device=device)
+            alias = torch.empty(n_arcs, dtype=torch.int32, device=device) if keep_tables else None
+            work = torch.empty(n_arcs, dtype=torch.int32, device=device)
+            n_zero = C.c_int64(0)
+            _lib.check(lib.n2v_alias_build(_lib.ptr(g.vtx), _lib.ptr(g.col), _lib.ptr(g.weight), g.n_vertices,
+                                           n_arcs, _lib.SUM_MODE[sum_mode], _lib.ptr(alias), _lib.ptr(probs),
+                                           _lib.ptr(g.arcs), _lib.ptr(work), C.byref(n_zero), stream),
+                       "n2v_alias_build")
+            if keep_tables:
+                g.alias, g.probs = alias, probs
+        g._make_struct()
+        return g
+
+    def _make_struct(self):
+        st = _lib.Graph()
+        st.n_vertices, st.n_arcs, st.flags = self.n_vertices, self.n_arcs, self.flags
+        st.n_parts, st.part_size = 1, max(self.n_vertices, 1)
+        st.parts[0].vtx = self.vtx.data_ptr()
+        st.parts[0].arcs = self.arcs.data_ptr()
+        st.parts[0].col = self.col.data_ptr()
+        st.parts[0].weight = self.weight.data_ptr()
+        self._struct = st
+
+    # ------------------------------------------------------------------ views
+    @property
+    def struct(self) -> "_lib.Graph":
+        return self._struct
+
+    def degrees(self) -> torch.Tensor:
+        return self.vtx[:, 2].clone()
+
+    def bases(self) -> torch.Tensor:
+        return self.vtx[:, :2].contiguous().view(torch.int64).view(-1)
+
+    def start_vertices(self) -> torch.Tensor:
+        """Vertices with at least one out-arc, ascending -- ``walk_start = df_adj[["id"]]``
+        (fugue.py:132): only they start walks."""
+        return torch.nonzero(self.vtx[:, 2] != 0).view(-1).to(torch.int32)
+
+    def nbytes(self) -> int:
+        return sum(int(t.numel()) * t.element_size() for t in (self.vtx, self.arcs, self.col, self.weight))
+
+    def to_host(self) -> Dict[str, np.ndarray]:
+        """Plain host arrays (for tests and the oracle's replay)."""
+        vtx = self.vtx.cpu().numpy()
+        arcs = self.arcs.cpu().numpy()
+        out = {
+            "base": vtx[:, :2].copy().view(np.uint64).reshape(-1),
+            "deg": vtx[:, 2].copy().view(np.uint32),
+            "wsum": vtx[:, 3].copy().view(np.float32),
+            "thr": arcs[:, 0].copy().view(np.uint32),
+            "dst": arcs[:, 1].copy(),
+            "alias_dst": arcs[:, 2].copy(),
+            "alias_idx": arcs[:, 3].copy(),
+            "col": self.col.cpu().numpy(),
+            "weight": self.weight.cpu().numpy(),
+        }
+        if self.alias is not None:
+            out["alias"] = self.alias.cpu().numpy()
+            out["probs"] = self.probs.cpu().numpy()
+        return out
+
+    # ------------------------------------------------------------------ K2
+    def walk(self, start, num_walks: int, walk_length: int, return_param: float = 1.0,
+             inout_param: float = 1.0, seed: Optional[int] = None, collect_stats: bool = False,
+             out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, Optional[Dict[str, int]]]:
+        """Launch the walk kernel.  Returns (walks[W, L+1] view of a pitch-padded buffer,
+        alive[W] bool, stats or None).  Row w = start index * num_walks + walk number."""
+        lib = _lib.load()
+        if return_param == 0 or inout_param == 0:
+            raise ValueError(f"Zero return ({return_param}) or inout ({inout_param}) parameter!")
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little")
+        with torch.cuda.device(self.device):
+            start_t = _as_device_i32(start, self.device)
+            n_start = int(start_t.numel())
+            W = n_start * int(num_walks)
+            pitch = (int(walk_length) + 1 + 7) // 8 * 8
+            if out is None:
+                out = torch.empty((W, pitch), dtype=torch.int32, device=self.device)
+            elif out.shape != (W, pitch) or out.dtype != torch.int32 or not out.is_contiguous():
+                raise ValueError(f"out must be a contiguous int32 tensor of shape {(W, pitch)}")
+            alive = torch.empty(W, dtype=torch.uint8, device=self.device)
+            stats = torch.zeros(8, dtype=torch.int64, device=self.device) if collect_stats else None
+            _lib.check(lib.n2v_walk(C.byref(self._struct), _lib.ptr(start_t), n_start, int(num_walks),
+                                    int(walk_length), float(return_param), float(inout_param),
+                                    C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), _lib.ptr(out), pitch, _lib.ptr(alive),
+                                    _lib.ptr(stats), _lib.current_stream_ptr()), "n2v_walk")
+            st = None
+            if collect_stats:
+                st = dict(zip(_lib.WALK_STAT_NAMES, stats.cpu().tolist()))
+        return out[:, : walk_length + 1], alive.bool(), st
+
+
+def walk_consts(return_param: float, inout_param: float, flags: int) -> "_lib.WalkConsts":
+    """Host-only: the sampling constants n2v_walk will use (no GPU needed)."""
+    c = _lib.WalkConsts()
+    _lib.check(_lib.load().n2v_walk_consts(float(return_param), float(inout_param), int(flags), C.byref(c)))
+    return c

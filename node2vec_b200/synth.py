@@ -1,0 +1,98 @@
+"""Synthetic graphs of the shapes BASELINE.json names (there is no network for datasets).
+
+All generators are seeded and return SYMMETRISED, de-duplicated, loop-free arc lists
+(src, dst) so that no walker dies; weights are implicit 1.0.
+"""
+import os
+from typing import Tuple
+
+import numpy as np
+
+
+def _symmetrise(a: np.ndarray, b: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    src = np.concatenate([a, b]).astype(np.int32)
+    dst = np.concatenate([b, a]).astype(np.int32)
+    return src, dst
+
+
+def erdos_renyi(n: int = 10000, m: int = 100000, seed: int = 42) -> Tuple[np.ndarray, np.ndarray]:
+    """BASELINE configs[0]: G(n, m) uniform -- exactly m distinct undirected edges."""
+    rng = np.random.default_rng(seed)
+    keys = np.zeros(0, dtype=np.int64)
+    while len(keys) < m:
+        a = rng.integers(0, n, 2 * (m - len(keys)) + 16)
+        b = rng.integers(0, n, len(a))
+        lo, hi = np.minimum(a, b), np.maximum(a, b)
+        k = (lo.astype(np.int64) << 32 | hi)[lo != hi]
+        keys = np.unique(np.concatenate([keys, k]))
+    keys = rng.permutation(keys)[:m]
+    return _symmetrise((keys >> 32).astype(np.int64), (keys & 0xFFFFFFFF).astype(np.int64))
+
+
+def blogcatalog_like(n: int = 10000, m: int = 334000, seed: int = 42) -> Tuple[np.ndarray, np.ndarray]:
+    """BASELINE configs[1]: a 10k-vertex power-law graph with clustering, thinned to m
+    undirected edges (Holme-Kim growth, 34 links per new vertex, triad probability 0.3;
+    max degree ~1.7k).  Cached under /tmp because the generator takes a few seconds."""
+    cache = f"/tmp/n2v_blogcatalog_like_{n}_{m}_{seed}.npz"
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return z["src"], z["dst"]
+    import networkx as nx
+    g = nx.powerlaw_cluster_graph(n, 34, 0.3, seed=seed)
+    e = np.array(g.edges(), dtype=np.int64)
+    rng = np.random.default_rng(seed)
+    e = e[rng.permutation(len(e))]
+    if len(e) > m:
+        deg = np.bincount(e.reshape(-1), minlength=n)
+        keep = np.ones(len(e), dtype=bool)
+        drop = len(e) - m
+        for i in range(len(e)):
+            if drop == 0:
+                break
+            a, b = e[i]
+            if deg[a] > 1 and deg[b] > 1:
+                keep[i] = False
+                deg[a] -= 1
+                deg[b] -= 1
+                drop -= 1
+        e = e[keep]
+    src, dst = _symmetrise(e[:, 0], e[:, 1])
+    try:
+        np.savez(cache, src=src, dst=dst)
+    except OSError:
+        pass
+    return src, dst
+
+
+def rmat_device(scale: int, edge_factor: int = 16, seed: int = 42, device=None,
+                abcd=(0.57, 0.19, 0.19, 0.05), hotspots: int = 0, hotspot_degree: int = 0):
+    """Graph500-style R-MAT generated ON THE DEVICE (torch ops; this is input synthesis, not
+    the hot path): 2^scale vertices, edge_factor * 2^scale undirected edges before
+    de-duplication; optional injected hotspot vertices.  Returns (src, dst) int32 CUDA
+    tensors, symmetrised, unique, loop-free."""
+    import torch
+    device = torch.device(device if device is not None else "cuda")
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    n_edges = edge_factor << scale
+    a, b, c, _ = abcd
+    src = torch.zeros(n_edges, dtype=torch.int64, device=device)
+    dst = torch.zeros(n_edges, dtype=torch.int64, device=device)
+    for _ in range(scale):
+        r = torch.rand(n_edges, device=device, generator=gen)
+        src = (src << 1) | (r >= a + b).long()
+        dst = (dst << 1) | (((r >= a) & (r < a + b)) | (r >= a + b + c)).long()
+    # scramble ids so hubs are not clustered at small ids
+    perm = torch.randperm(1 << scale, device=device, generator=gen)
+    src, dst = perm[src], perm[dst]
+    if hotspots > 0:
+        n = 1 << scale
+        hubs = torch.randint(0, n, (hotspots,), device=device, generator=gen)
+        hs = hubs.repeat_interleave(hotspot_degree)
+        hd = torch.randint(0, n, (hotspots * hotspot_degree,), device=device, generator=gen)
+        src, dst = torch.cat([src, hs]), torch.cat([dst, hd])
+    lo, hi = torch.minimum(src, dst), torch.maximum(src, dst)
+    keys = torch.unique(((lo << 32) | hi)[lo != hi])
+    lo, hi = keys >> 32, keys & 0xFFFFFFFF
+    del keys
+    return torch.cat([lo, hi]).to(torch.int32), torch.cat([hi, lo]).to(torch.int32)

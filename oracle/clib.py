@@ -1,0 +1,202 @@
+"""ctypes front-end of the C oracle (oracle/csrc/n2v_oracle.c).  TEST INFRASTRUCTURE.
+
+``load()`` builds ``oracle/_build/libn2v_oracle.so`` with the Makefile when it is
+missing (gcc only) and returns thin numpy wrappers.  Threaded variants fan ranges out
+over Python threads (ctypes drops the GIL) because this image has no OpenMP runtime.
+"""
+import ctypes as C
+import os
+import subprocess
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_build", "libn2v_oracle.so")
+
+SUM_MODE = {"naive": 0, "neumaier": 1}
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(HERE, "csrc", f) for f in ("n2v_oracle.c", "sgns_ref.c")]
+    stale = (not os.path.exists(SO)) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", HERE, "-B"], stdout=subprocess.DEVNULL)
+    return SO
+
+
+class WalkConsts(C.Structure):
+    _fields_ = [("t_ret", C.c_uint64), ("t_nbr", C.c_uint64), ("t_far", C.c_uint64),
+                ("fold_gain", C.c_float), ("fold_mode", C.c_int32), ("max_trials", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def load():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(SO)
+        _lib.orc_alias_tables_csr.restype = C.c_int64
+        _lib.orc_reference_walk.restype = C.c_int64
+    return _lib
+
+
+def csr_from_arcs(src, dst, wt, n_vertices=None):
+    """(src, dst)-sorted CSR with stable ties -- numpy twin of build_adjacency."""
+    src = np.asarray(src, dtype=np.int64)
+    dst = np.asarray(dst, dtype=np.int64)
+    wt = np.ones(len(src), dtype=np.float64) if wt is None else np.asarray(wt, dtype=np.float64)
+    if n_vertices is None:
+        n_vertices = int(max(src.max(initial=-1), dst.max(initial=-1)) + 1)
+    order = np.lexsort((dst, src))  # stable
+    deg = np.bincount(src, minlength=n_vertices)
+    row_ptr = np.zeros(n_vertices + 1, dtype=np.int64)
+    np.cumsum(deg, out=row_ptr[1:])
+    return row_ptr, dst[order].astype(np.int32), wt[order].copy(), order
+
+
+def alias_tables(weights, mode="naive"):
+    lib = load()
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    alias = np.zeros(len(w), dtype=np.int32)
+    probs = np.zeros(len(w), dtype=np.float64)
+    rc = lib.orc_alias_tables(_ptr(w, C.c_double), C.c_int64(len(w)), SUM_MODE[mode],
+                              _ptr(alias, C.c_int32), _ptr(probs, C.c_double))
+    if rc != 0:
+        raise ZeroDivisionError("float division by zero")
+    return alias, probs
+
+
+def alias_tables_csr(row_ptr, weights, mode="naive", threads=1):
+    lib = load()
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    alias = np.zeros(len(w), dtype=np.int32)
+    probs = np.zeros(len(w), dtype=np.float64)
+    nv = len(row_ptr) - 1
+
+    def run(rng):
+        return lib.orc_alias_tables_csr(_ptr(row_ptr, C.c_int64), _ptr(w, C.c_double), C.c_int64(rng[0]),
+                                        C.c_int64(rng[1]), SUM_MODE[mode], _ptr(alias, C.c_int32),
+                                        _ptr(probs, C.c_double))
+    bounds = [(nv * i // threads, nv * (i + 1) // threads) for i in range(threads)]
+    if threads == 1:
+        bad = run(bounds[0])
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            bad = sum(ex.map(run, bounds))
+    return alias, probs, int(bad)
+
+
+def edge_alias_tables(row_ptr, col, w, prev, cur, p, q, mode="naive"):
+    lib = load()
+    n = int(row_ptr[cur + 1] - row_ptr[cur])
+    alias = np.zeros(n, dtype=np.int32)
+    probs = np.zeros(n, dtype=np.float64)
+    rc = lib.orc_edge_alias_tables(_ptr(row_ptr, C.c_int64), _ptr(col, C.c_int32), _ptr(w, C.c_double),
+                                   C.c_int32(prev), C.c_int32(cur), C.c_double(p), C.c_double(q),
+                                   SUM_MODE[mode], _ptr(alias, C.c_int32), _ptr(probs, C.c_double))
+    if rc == -2:
+        raise ValueError(f"Zero return ({p}) or inout ({q}) parameter!")
+    if rc != 0:
+        raise ZeroDivisionError("float division by zero")
+    return alias, probs
+
+
+def mt_random(seed, n):
+    lib = load()
+    out = np.zeros(n, dtype=np.float64)
+    lib.orc_mt_random(C.c_uint64(seed), C.c_int64(n), _ptr(out, C.c_double))
+    return out
+
+
+def reference_walk(row_ptr, col, w, start, num_walks, walk_length, p, q, mode="naive",
+                   random_seed=None, threads=1):
+    """The reference's walk (C port).  threads == 1 and a seed reproduce the Python oracle /
+    the reference exactly; threads > 1 is for timing (one MT stream per range)."""
+    lib = load()
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    start = np.ascontiguousarray(start, dtype=np.int32)
+    W = len(start) * num_walks
+    walks = np.empty((W, walk_length + 1), dtype=np.int32)
+    alive = np.empty(W, dtype=np.uint8)
+    max_deg = int(np.diff(row_ptr).max(initial=0))
+    has_seed = random_seed is not None
+    base_seed = int(random_seed) if has_seed else int.from_bytes(os.urandom(4), "little")
+
+    def run(i):
+        lo, hi = W * i // threads, W * (i + 1) // threads
+        return lib.orc_reference_walk(
+            _ptr(row_ptr, C.c_int64), _ptr(col, C.c_int32), _ptr(w, C.c_double), C.c_int64(max_deg),
+            _ptr(start, C.c_int32), C.c_int64(len(start)), C.c_int32(num_walks), C.c_int32(walk_length),
+            C.c_double(p), C.c_double(q), SUM_MODE[mode], C.c_int(1 if has_seed else 0),
+            C.c_uint64(base_seed + 100 * i), C.c_int64(lo), C.c_int64(hi),
+            _ptr(walks, C.c_int32), _ptr(alive, C.c_uint8))
+    if threads == 1:
+        run(0)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(run, range(threads)))
+    return walks, alive.astype(bool)
+
+
+def philox(key, ctr):
+    lib = load()
+    k = (C.c_uint32 * 2)(*key)
+    c = (C.c_uint32 * 4)(*ctr)
+    o = (C.c_uint32 * 4)()
+    lib.orc_philox4x32_10(k, c, o)
+    return list(o)
+
+
+def walk_consts(p, q, graph_flags):
+    lib = load()
+    c = WalkConsts()
+    if lib.orc_walk_consts_for(C.c_double(p), C.c_double(q), C.c_uint32(graph_flags), C.byref(c)) != 0:
+        raise ValueError(f"Zero return ({p}) or inout ({q}) parameter!")
+    return c
+
+
+def replay_walk(base, deg, arc_thr, arc_dst, arc_alias_dst, col, weight, graph_flags, p, q, start,
+                num_walks, walk_length, seed, pitch=None, threads=1):
+    """Host replay of the device sampler (bit-exact twin of n2v_walk)."""
+    lib = load()
+    base = np.ascontiguousarray(base, dtype=np.uint64)
+    deg = np.ascontiguousarray(deg, dtype=np.uint32)
+    arc_thr = np.ascontiguousarray(arc_thr, dtype=np.uint32)
+    arc_dst = np.ascontiguousarray(arc_dst, dtype=np.int32)
+    arc_alias_dst = np.ascontiguousarray(arc_alias_dst, dtype=np.int32)
+    col = np.ascontiguousarray(col, dtype=np.int32)
+    weight = np.ascontiguousarray(weight, dtype=np.float64)
+    start = np.ascontiguousarray(start, dtype=np.int32)
+    if pitch is None:
+        pitch = (walk_length + 1 + 7) // 8 * 8
+    W = len(start) * num_walks
+    walks = np.empty((W, pitch), dtype=np.int32)
+    alive = np.empty(W, dtype=np.uint8)
+    consts = walk_consts(p, q, graph_flags)
+    stats = np.zeros((threads, 8), dtype=np.uint64)
+
+    def run(i):
+        lo, hi = W * i // threads, W * (i + 1) // threads
+        st = stats[i]
+        lib.orc_replay_walk(
+            _ptr(base, C.c_uint64), _ptr(deg, C.c_uint32), _ptr(arc_thr, C.c_uint32), _ptr(arc_dst, C.c_int32),
+            _ptr(arc_alias_dst, C.c_int32), _ptr(col, C.c_int32), _ptr(weight, C.c_double), C.byref(consts),
+            C.c_double(p), C.c_double(q), _ptr(start, C.c_int32), C.c_int64(len(start)), C.c_int32(num_walks),
+            C.c_int32(walk_length), C.c_uint64(seed), C.c_int64(lo), C.c_int64(hi), _ptr(walks, C.c_int32),
+            C.c_int64(pitch), _ptr(alive, C.c_uint8), _ptr(st, C.c_uint64))
+    if threads == 1:
+        run(0)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(run, range(threads)))
+    names = ["steps", "trials", "probes", "searches", "fold_hits", "fallbacks", "dead", "reserved"]
+    return walks, alive.astype(bool), dict(zip(names, stats.sum(axis=0).tolist()))

@@ -1,0 +1,172 @@
+"""CPU-only checks of the boundary: the shared library loads, exports every symbol that
+include/n2v_b200.h declares, host-only entry points behave, and the host facade validates
+arguments like the reference does.  No compute calls (there is no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import pandas as pd
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "n2v_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(n2v_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from node2vec_b200 import _lib
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    names = _declared_functions()
+    assert "n2v_walk" in names and "n2v_alias_build" in names and len(names) >= 9
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/n2v_b200.h but not exported"
+
+
+def test_abi_version_and_struct_sizes(lib):
+    from node2vec_b200 import _lib
+    assert lib.n2v_abi_version() == 1
+    assert C.sizeof(_lib.GraphPart) == 32
+    assert C.sizeof(_lib.Graph) == 8 + 8 + 4 + 4 + 8 + 32 * 16
+    assert C.sizeof(_lib.WalkConsts) == 40
+
+
+def test_walk_consts_host_only(lib):
+    from node2vec_b200 import graph
+    from oracle import clib
+    for p, q in [(1.0, 1.0), (1.0, 0.5), (0.25, 4.0), (4.0, 0.25), (0.5, 0.5), (1e-3, 1e3), (3.0, 7.0)]:
+        for flags in (0, 7, 3, 5):
+            a, b = graph.walk_consts(p, q, flags), clib.walk_consts(p, q, flags)
+            assert (a.t_ret, a.t_nbr, a.t_far, a.fold_mode, a.max_trials) == \
+                   (b.t_ret, b.t_nbr, b.t_far, b.fold_mode, b.max_trials)
+            assert a.fold_gain == b.fold_gain
+            assert 1 <= a.t_ret <= 2 ** 32 and 1 <= a.t_nbr <= 2 ** 32 and 1 <= a.t_far <= 2 ** 32
+    c = graph.walk_consts(1.0, 1.0, 0)
+    assert c.t_ret == c.t_nbr == c.t_far == 2 ** 32 and c.fold_mode == 0
+    c = graph.walk_consts(0.25, 4.0, 7)                     # fold: envelope stays at max(1, 1/q) = 1
+    assert c.fold_mode == 1 and c.t_nbr == 2 ** 32 and c.t_far == 2 ** 30 and abs(c.fold_gain - 3.0) < 1e-6
+    c = graph.walk_consts(0.25, 4.0, 0)                     # no fold possible: envelope 1/p = 4
+    assert c.fold_mode == 0 and c.t_ret == 2 ** 32 and c.t_nbr == 2 ** 30 and c.t_far == 2 ** 28
+    with pytest.raises(ValueError):
+        graph.walk_consts(0.0, 1.0, 0)
+    with pytest.raises(ValueError):
+        graph.walk_consts(1.0, 0.0, 0)
+    assert b"Zero return" in lib.n2v_last_error()
+
+
+def test_product_has_no_cpu_fallback():
+    """Without a GPU every compute entry of the host facade must fail loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from node2vec_b200 import _lib, fugue, randomwalk
+    with pytest.raises(_lib.N2VError):
+        randomwalk.generate_alias_tables([0.5, 0.8, 1.0])
+    df = pd.DataFrame({"src": [0, 1], "dst": [1, 0], "weight": [1.0, 1.0]})
+    with pytest.raises(_lib.N2VError):
+        fugue.random_walk(None, df, {})
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "node2vec_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "n2v_oracle" not in text, f
+
+
+def test_facade_argument_validation_matches_reference():
+    from node2vec_b200 import fugue, randomwalk
+    from node2vec_b200.constants import GENSIM_PARAMS, NODE2VEC_PARAMS, WORD2VEC_PARAMS
+    df = pd.DataFrame({"dst": ["a2", "b1"], "weight": [0.8, 1.1]})
+    with pytest.raises(ValueError):
+        fugue.trim_index(None, df, False)
+    good = pd.DataFrame({"src": [0, 1], "dst": [1, 0], "weight": [1.0, 1.0]})
+    params = {"num_walks": 2}
+    with pytest.raises(ValueError):
+        fugue.random_walk(None, good, params, good)                 # walk_seed lacks "id"
+    assert params["walk_length"] == 20 and params["return_param"] == 1.0   # defaults merged in place first
+    with pytest.raises(ValueError):
+        randomwalk.generate_edge_alias_tables(0, set(), ([1, 2], [1.0]))
+    with pytest.raises(ValueError):
+        randomwalk.generate_edge_alias_tables(0, set(), ([1], [1.0]), 0)
+    # tests/test_constants.py of the reference
+    assert isinstance(NODE2VEC_PARAMS["num_walks"], int) and isinstance(NODE2VEC_PARAMS["walk_length"], int)
+    assert isinstance(NODE2VEC_PARAMS["return_param"], float) and isinstance(NODE2VEC_PARAMS["inout_param"], float)
+    assert isinstance(WORD2VEC_PARAMS["stepSize"], float)
+    for k in ["minCount", "numPartitions", "maxIter", "maxSentenceLength", "windowSize", "vectorSize"]:
+        assert isinstance(WORD2VEC_PARAMS[k], int)
+    assert isinstance(GENSIM_PARAMS["alpha"], float)
+    for k in ["min_count", "iter", "batch_words", "window", "size", "negative", "workers"]:
+        assert isinstance(GENSIM_PARAMS[k], int)
+
+
+def test_value_types_reference_goldens():
+    """tests/test_randomwalk.py:16-49,53-90,94-128 serialisation goldens (pickle protocol 3)."""
+    from node2vec_b200.randomwalk import AliasProb, Neighbors, RandomPath
+    idx, weight = [0, 1, 2], [1.0, 0.2, 1.4]
+    code64 = "gANdcQAoSwBLAUsCZV1xAShHP/AAAAAAAABHP8mZmZmZmZpHP/ZmZmZmZmZlhnECLg=="
+    for nbs in (Neighbors((idx, weight)), Neighbors(code64)):
+        assert nbs.dst_id == idx and nbs.dst_wt == weight
+        assert list(nbs.items()) == [(0, 1.0), (1, 0.2), (2, 1.4)]
+        assert nbs.serialize() == code64
+        assert nbs.as_pandas().equals(pd.DataFrame({"dst": idx, "weight": weight}))
+    nbs = Neighbors(pd.DataFrame({"dst": [1, 2, 3], "weight": [0.1, 1.2, 0.8]}))
+    assert nbs.serialize() == "gANdcQAoSwFLAksDZV1xAShHP7mZmZmZmZpHP/MzMzMzMzNHP+mZmZmZmZplhnECLg=="
+    code = "gANdcQAoSwFLAGVdcQEoRz/lVVVVVVVVRz/wAAAAAAAAZYZxAi4="
+    for jq in (AliasProb(([1, 0], [0.6666666666666666, 1.0])), AliasProb(code),
+               AliasProb(pd.DataFrame({"alias": [1, 0], "probs": [0.6666666666666666, 1.0]}))):
+        assert jq.alias == [1, 0] and jq.probs == [0.6666666666666666, 1.0] and jq.serialize() == code
+    for path, code in [([-1, 0], "gANdcQAoSv////9LAGUu"), ([2, 1], "gANdcQAoSwJLAWUu"), ([0, 3], "gANdcQAoSwBLA2Uu")]:
+        for rp in (RandomPath(path), RandomPath(code)):
+            assert rp.path == path and rp.last_edge == (path[-2], path[-1])
+            assert rp.serialize() == code and str(rp) == str(path)
+
+
+def test_host_transformers():
+    from node2vec_b200.randomwalk import get_vertex_neighbors, initiate_random_walk, to_path, trim_hotspot_vertices
+    df = pd.DataFrame({"src": [3, 3, 3], "dst": [0, 1, 2], "weight": [1.0, 0.2, 1.4]})
+    res = next(iter(get_vertex_neighbors(df)))
+    assert res["id"] == 3
+    assert res["neighbors"] == "gANdcQAoSwBLAUsCZV1xAShHP/AAAAAAAABHP8mZmZmZmZpHP/ZmZmZmZmZlhnECLg=="
+    rows = list(trim_hotspot_vertices(df))
+    assert [r["dst"] for r in rows] == [0, 1, 2]
+    assert len(list(trim_hotspot_vertices(df, max_out_degree=2, random_seed=20))) == 2
+    it = iter(initiate_random_walk([{"id": 3}, {"id": 2}], 3))
+    for s in (3, 2):
+        for i in range(3):
+            a = next(it)
+            assert (a["src"], a["dst"], a["path"]) == (-1 - i, s, [-1 - i, s])
+    out = list(to_path([{"src": 0, "dst": 2, "path": [1, 0, 2]}]))
+    assert out == [{"src": 1, "walk": [1, 0, 2]}]
+
+
+def test_indexer_facade_bit_exact():
+    from node2vec_b200.indexer import index_graph_dense, index_graph_pandas
+    from tests.helpers import load_golden
+    for c in load_golden("indexer.json")["cases"]:
+        cols = {"src": c["src"], "dst": c["dst"]}
+        if c["weight"] is not None:
+            cols["weight"] = c["weight"]
+        e, n = index_graph_pandas(pd.DataFrame(cols), c["directed"])
+        assert e["src"].tolist() == c["edge_src"] and e["dst"].tolist() == c["edge_dst"]
+        assert [float(x).hex() for x in e["weight"]] == c["edge_weight"]
+        assert n["vertex_id"].tolist() == c["vertex_id"] and n["vertex_name"].tolist() == c["vertex_name"]
+    # reference tests/test_indexer.py:8-25
+    g = pd.DataFrame({"src": ["a1", "a2", "a3", "a4"], "dst": ["a2", "b1", "b2", "a1"]})
+    e, vid = index_graph_pandas(g, False)
+    assert len(vid) == 6 and len(e) == 8
+    with pytest.raises(ValueError):
+        index_graph_pandas(pd.DataFrame({"dst": ["a"], "weight": [1.0]}), True)
+    e, vid = index_graph_dense(pd.DataFrame({"src": ["b", "a"], "dst": ["c", "b"]}), True)
+    assert vid["id"].tolist() == [0, 1, 2] and vid["name"].tolist() == ["a", "b", "c"]
+    assert e["src"].tolist() == [1, 0] and e["dst"].tolist() == [2, 1]

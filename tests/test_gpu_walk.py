@@ -1,0 +1,444 @@
+"""GPU parity tests for the walk half (K0 csr_build, K1 alias_build, a4/a5/a6, K2 walk).
+
+Everything goes through the C ABI (ctypes -> libn2v_b200.so).  Integer/index results and
+the fp64 alias tables are compared BIT-EXACTLY with the oracle and with the golden
+fixtures produced by the unmodified reference; walk distributions are compared with the
+reference's transition law by chi-square at significance 1e-4 per cell group (the stated
+tolerance), and every GPU walk must equal its seeded host replay bit for bit.
+"""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import clib, ref_walk
+from tests.helpers import chi_square_ok, graph_flags, load_golden, pack_arcs, unhex
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def n2v():
+    import torch
+    assert torch.cuda.is_available()
+    from node2vec_b200 import _lib, fugue, graph, randomwalk
+    _lib.load()
+
+    class NS:
+        pass
+    ns = NS()
+    ns.torch, ns.lib, ns.graph, ns.rw, ns.fugue = torch, _lib, graph, randomwalk, fugue
+    return ns
+
+
+def _random_arcs(rng, n, m, weighted=True, sym=False, multi=False):
+    src = rng.integers(0, n, m)
+    dst = rng.integers(0, n, m)
+    keep = src != dst
+    src, dst = src[keep], dst[keep]
+    if not multi:
+        key = np.unique(src.astype(np.int64) << 32 | dst)
+        src, dst = (key >> 32).astype(np.int64), (key & 0xFFFFFFFF).astype(np.int64)
+        perm = rng.permutation(len(src))
+        src, dst = src[perm], dst[perm]
+    w = rng.uniform(0.1, 2.0, len(src)) if weighted else np.ones(len(src))
+    if sym:
+        a, b = np.minimum(src, dst), np.maximum(src, dst)
+        key, idx = np.unique(a.astype(np.int64) << 32 | b, return_index=True)
+        a, b, w = a[idx], b[idx], w[idx]
+        src, dst, w = np.concatenate([a, b]), np.concatenate([b, a]), np.concatenate([w, w])
+    return src, dst, w
+
+
+# ---------------------------------------------------------------------------------- K0
+@pytest.mark.parametrize("weighted,sym,multi", [(True, False, True), (False, True, False), (True, True, False),
+                                                (False, False, False)])
+def test_csr_build_matches_numpy(n2v, weighted, sym, multi):
+    rng = np.random.default_rng(5)
+    src, dst, w = _random_arcs(rng, 500, 6000, weighted, sym, multi)
+    g = n2v.graph.DeviceGraph.from_arcs(src, dst, w if weighted else None, n_vertices=520, keep_perm=True)
+    row_ptr, col, ws, order = clib.csr_from_arcs(src, dst, w, 520)
+    h = g.to_host()
+    deg = np.diff(row_ptr)
+    assert h["deg"].tolist() == deg.tolist()
+    assert h["base"][deg > 0].tolist() == row_ptr[:-1][deg > 0].tolist()
+    assert h["col"].tolist() == col.tolist()
+    assert h["weight"].view(np.uint64).tolist() == ws.view(np.uint64).tolist()
+    assert g.perm.cpu().numpy().tolist() == order.tolist()          # stable ties
+    assert g.flags == graph_flags(row_ptr, col, ws)
+    assert g.start_vertices().cpu().numpy().tolist() == np.flatnonzero(deg > 0).tolist()
+
+
+def test_csr_build_rejects_bad_ids(n2v):
+    with pytest.raises(ValueError):
+        n2v.graph.DeviceGraph.from_arcs([0, 1, 7], [1, 0, 2], None, n_vertices=5)
+
+
+def test_empty_graph(n2v):
+    g = n2v.graph.DeviceGraph.from_arcs(np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32), None, n_vertices=4)
+    assert g.n_arcs == 0 and g.start_vertices().numel() == 0
+    walks, alive, _ = g.walk(g.start_vertices(), 3, 4)
+    assert walks.shape == (0, 5)
+
+
+# ---------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("mode", ["naive", "neumaier"])
+def test_alias_build_bit_exact_vs_oracle(n2v, mode):
+    rng = np.random.default_rng(6)
+    src, dst, w = _random_arcs(rng, 2000, 60000, True, False, True)
+    w[rng.integers(0, len(w), 500)] = 1.0                    # exact ties / probs == 1.0 cases
+    hub = np.full(30000, 7)                                   # a 30k-degree hub
+    src = np.concatenate([src, hub]); dst = np.concatenate([dst, rng.integers(0, 2000, 30000)])
+    w = np.concatenate([w, rng.pareto(1.5, 30000) + 0.01])
+    g = n2v.graph.DeviceGraph.from_arcs(src, dst, w, n_vertices=2000, sum_mode=mode, keep_tables=True)
+    row_ptr, col, ws, _ = clib.csr_from_arcs(src, dst, w, 2000)
+    alias, probs, bad = clib.alias_tables_csr(row_ptr, ws, mode, threads=4)
+    assert bad == 0
+    h = g.to_host()
+    assert np.array_equal(h["alias"], alias)
+    assert np.array_equal(h["probs"].view(np.uint64), probs.view(np.uint64))
+    thr, adst, aalias = pack_arcs(row_ptr, col, alias, probs)
+    assert np.array_equal(h["thr"], thr) and np.array_equal(h["dst"], adst)
+    assert np.array_equal(h["alias_dst"], aalias) and np.array_equal(h["alias_idx"], alias)
+    wsum = np.array([np.float32(ref_walk.float_sum(ws[a:b].tolist())) for a, b in zip(row_ptr[:-1], row_ptr[1:])],
+                    dtype=np.float32)
+    assert np.array_equal(h["wsum"][np.diff(row_ptr) > 0], wsum[np.diff(row_ptr) > 0])
+
+
+@pytest.mark.parametrize("label", ["native", "naive"])
+def test_alias_build_golden(n2v, label):
+    """Every golden weight vector of the reference becomes one vertex of a graph."""
+    fx = load_golden("alias_tables.json")
+    mode = "naive" if label == "naive" else fx["native_sum_mode"]
+    src, dst, w = [], [], []
+    for i, case in enumerate(fx["cases"]):
+        ws = unhex(case["weights"])
+        src += [i] * len(ws); dst += list(range(len(ws))); w += ws
+    nv = max(max(dst) + 1, len(fx["cases"]))
+    g = n2v.graph.DeviceGraph.from_arcs(src, dst, w, n_vertices=nv, sum_mode=mode, keep_tables=True)
+    h = g.to_host()
+    for i, case in enumerate(fx["cases"]):
+        b, n = int(h["base"][i]), int(h["deg"][i])
+        assert h["alias"][b:b + n].tolist() == case[label]["alias"]
+        assert [x.hex() for x in h["probs"][b:b + n].tolist()] == case[label]["probs"]
+
+
+def test_zero_weight_vertex_raises(n2v):
+    with pytest.raises(ValueError):
+        n2v.graph.DeviceGraph.from_arcs([0, 0, 1], [1, 2, 0], [0.0, 0.0, 1.0], n_vertices=3)
+    with pytest.raises(ZeroDivisionError):
+        n2v.rw.generate_alias_tables([0.0, 0.0])
+    with pytest.raises(ZeroDivisionError):
+        n2v.rw.generate_alias_tables([])
+
+
+# ---------------------------------------------------------------- a3/a4/a5/a6 via the facade
+def test_reference_kats_through_facade(n2v):
+    """The reference's own tests/test_randomwalk.py vectors, against node2vec_b200.randomwalk."""
+    rw = n2v.rw
+    for weights, alias, probs in [([0.5, 0.8, 1.0], [2, 0, 1], [0.6521739, 1.0, 0.9565217]),
+                                  ([0.5, 0.2], [0, 0], [1.0, 0.5714285714285715]),
+                                  ([0.2], [0], [1.0]), ([1.0], [0], [1.0])]:
+        a, p = rw.generate_alias_tables(weights)
+        assert a == alias
+        np.testing.assert_almost_equal(p, probs, decimal=7)
+    for prev, shared, nbrs, p_, q_, alias, probs in [
+            (0, {2}, ([0, 2], [0.5, 0.2]), 1.0, 1.0, [0, 0], [1.0, 0.5714285714285715]),
+            (1, set(), ([1], [0.2]), 0.8, 1.5, [0], [1.0]),
+            (3, set(), ([1, 3], [0.5, 1.0]), 2.0, 4.0, [1, 0], [0.4, 1.0])]:
+        a, p = rw.generate_edge_alias_tables(prev, shared, nbrs, p_, q_)
+        assert a == alias
+        np.testing.assert_almost_equal(p, probs, decimal=7)
+        pytest.raises(ValueError, rw.generate_edge_alias_tables, prev, shared, nbrs, 0)
+        pytest.raises(ValueError, rw.generate_edge_alias_tables, prev, shared, nbrs, 1.0, 0)
+        pytest.raises(ValueError, rw.generate_edge_alias_tables, prev, shared, (nbrs[0], nbrs[1][:-1]))
+    # AliasProb / RandomPath at seed 20 (tests/test_randomwalk.py:53-128)
+    nbs = rw.Neighbors(([11, 22], [1.0, 0.5]))
+    jq = rw.AliasProb(([1, 0], [0.6666666666666666, 1.0]))
+    random.seed(20)
+    r1 = random.random()
+    assert nbs.dst_id[jq.sampling_from_alias_wiki(r1)] == 22
+    assert nbs.dst_id[jq.sampling_from_alias(r1, random.random())] == 22
+    for path, ids, alias, probs, result in [([-1, 0], [1, 3], [1, 0], [0.6666666666666666, 1.0], [0, 3]),
+                                            ([2, 1], [0, 2], [0, 0], [1.0, 0.5714285714285715], [2, 1, 0]),
+                                            ([0, 3], [0], [0], [1.0], [0, 3, 0])]:
+        random.seed(20)
+        assert rw.RandomPath(path).append(ids, rw.AliasProb((alias, probs)), random.random()).path == result
+
+
+def test_edge_alias_tables_golden_bit_exact(n2v):
+    fx = load_golden("edge_alias_tables.json")
+    cs = fx["cases"]
+    for label in ("native", "naive"):
+        mode = "naive" if label == "naive" else fx["native_sum_mode"]
+        for c in cs:  # p, q differ per case: one launch each
+            a, p = n2v.rw.edge_alias_tables_batch([c["prev"]], [set(c["prev_out"])], [c["ids"]],
+                                                  [unhex(c["weights"])], c["p"], c["q"], mode)[0]
+            assert a == c[label]["alias"]
+            assert [x.hex() for x in p] == c[label]["probs"]
+
+
+def test_samplers_golden(n2v):
+    fx = load_golden("samplers.json")
+    d = fx["draws"]
+    two = n2v.rw.alias_draw([c["alias"] for c in d], [unhex(c["probs"]) for c in d],
+                            [float.fromhex(c["r1"]) for c in d], [float.fromhex(c["r2"]) for c in d])
+    one = n2v.rw.alias_draw([c["alias"] for c in d], [unhex(c["probs"]) for c in d],
+                            [float.fromhex(c["r1"]) for c in d], None)
+    assert two.tolist() == [c["two"] for c in d]
+    assert one.tolist() == [c["one"] for c in d]
+    for c in fx["appends"]:
+        r2 = None if c["r2"] is None else float.fromhex(c["r2"])
+        got = n2v.rw.RandomPath(c["path"]).append(c["ids"], n2v.rw.AliasProb((c["alias"], unhex(c["probs"]))),
+                                                  float.fromhex(c["r1"]), r2).path
+        assert got == c["out"]
+
+
+def test_next_step_random_walk_reference_rows(n2v):
+    """tests/test_randomwalk.py:268-306 against the facade (seeded MT, device tables + draws)."""
+    rw = n2v.rw
+    dst_neighbors = [rw.Neighbors(([0, 2, 4], [0.5, 0.9, 1.0])).serialize(),
+                     rw.Neighbors(([0, 3], [1.2, 0.9])).serialize(),
+                     rw.Neighbors(([0, 3], [1.2, 0.9])).serialize()]
+    src_neighbors = [rw.Neighbors(([2], [1.0])).serialize(), None, None]
+    src, dst, path = [0, 0, -1], [1, 2, 2], [[3, 0, 1], [2, 0, 2], [-1, 2]]
+    rows = [{"src": src[i], "dst": dst[i], "path": path[i], "dst_neighbors": dst_neighbors[i],
+             "src_neighbors": src_neighbors[i]} for i in range(3)]
+    for i, seed, want in [(0, 1000, (1, 4, [3, 0, 1, 4])), (1, 10, (2, 3, [2, 0, 2, 3])), (2, 20, (2, 3, [2, 3]))]:
+        ans = list(rw.next_step_random_walk([rows[i]], 1.0, 1.0, seed))[0]
+        assert (ans["src"], ans["dst"], ans["path"]) == want
+    fx = load_golden("walks.json")["single_rows"]
+    assert [(r["src"], r["dst"], r["path"]) for r in fx] == [(1, 4, [3, 0, 1, 4]), (2, 3, [2, 0, 2, 3]), (2, 3, [2, 3])]
+
+
+def test_whole_reference_walks_through_row_facade(n2v):
+    """Chain the facade's transformer-level functions exactly as fugue.random_walk does and
+    reproduce the reference's seeded walks (golden, naive sum mode)."""
+    rw = n2v.rw
+    fx = load_golden("walks.json")
+    for rec in fx["walks"][:4]:
+        import pandas as pd
+        df = pd.DataFrame({"src": rec["src"], "dst": rec["dst"], "weight": unhex(rec["weight"])})
+        adj = {}
+        for s, part in df.groupby("src", sort=True):
+            part = part.sort_values("dst", kind="stable").reset_index(drop=True)
+            row = next(iter(rw.get_vertex_neighbors(part)))
+            adj[int(row["id"])] = row["neighbors"]
+        starts = sorted(adj)
+        if rec["walk_seed"] is not None:
+            starts = [v for v in starts if v in set(rec["walk_seed"])]
+        P = {"num_walks": 10, "walk_length": 20, "return_param": 1.0, "inout_param": 1.0, **rec["params"]}
+        rows = [dict(r) for r in rw.initiate_random_walk([{"id": v} for v in starts], P["num_walks"])]
+        for _ in range(P["walk_length"]):
+            joined = [{"src": r["src"], "path": r["path"], "src_neighbors": adj.get(r["src"]),
+                       "dst_neighbors": adj[r["dst"]]} for r in rows if r["dst"] in adj]
+            rows = list(rw.next_step_random_walk(joined, P["return_param"], P["inout_param"], rec["random_seed"]))
+        assert [r["walk"] for r in rw.to_path(rows)] == rec["naive"], rec["graph"]
+
+
+# ---------------------------------------------------------------------------------- K2
+def _replay(g, p, q, start, num_walks, L, seed, threads=4):
+    h = g.to_host()
+    return clib.replay_walk(h["base"], h["deg"], h["thr"], h["dst"], h["alias_dst"], h["col"], h["weight"],
+                            g.flags, p, q, start, num_walks, L, seed, threads=threads)
+
+
+WALK_CASES = [
+    # n, m, weighted, sym, multi, p, q, num_walks, L
+    (300, 3000, True, False, True, 1.0, 1.0, 3, 9),
+    (300, 3000, False, True, False, 1.0, 0.5, 4, 20),
+    (300, 3000, False, True, False, 0.25, 4.0, 4, 40),      # fold path
+    (300, 3000, True, True, False, 0.25, 4.0, 2, 17),       # weighted: no fold, wide envelope
+    (300, 2000, True, False, False, 4.0, 0.25, 2, 8),       # directed with sinks
+    (50, 400, False, True, False, 100.0, 1000.0, 6, 5),      # fallback scans
+    (2000, 40000, False, True, False, 0.5, 2.0, 2, 80),
+]
+
+
+@pytest.mark.parametrize("case", WALK_CASES)
+def test_walk_equals_host_replay(n2v, case):
+    n, m, weighted, sym, multi, p, q, nw, L = case
+    rng = np.random.default_rng(hash(case) % 2 ** 31)
+    src, dst, w = _random_arcs(rng, n, m, weighted, sym, multi)
+    g = n2v.graph.DeviceGraph.from_arcs(src, dst, w if weighted else None, n_vertices=n + 3)
+    consts = n2v.graph.walk_consts(p, q, g.flags)
+    oc = clib.walk_consts(p, q, g.flags)
+    assert (consts.t_ret, consts.t_nbr, consts.t_far, consts.fold_mode, consts.max_trials) == \
+        (oc.t_ret, oc.t_nbr, oc.t_far, oc.fold_mode, oc.max_trials)
+    assert np.float32(consts.fold_gain) == np.float32(oc.fold_gain)
+    start = g.start_vertices()
+    walks, alive, stats = g.walk(start, nw, L, p, q, seed=4242, collect_stats=True)
+    rw, ra, rs = _replay(g, p, q, start.cpu().numpy(), nw, L, 4242)
+    full = walks._base if walks._base is not None else walks
+    assert np.array_equal(alive.cpu().numpy(), ra)
+    assert np.array_equal(full.cpu().numpy(), rw)                       # whole pitch-padded matrix, -1 padding too
+    for k in ("steps", "trials", "probes", "searches", "fold_hits", "fallbacks", "dead"):
+        assert stats[k] == rs[k], k
+    # stats-free launch (the timed variant) gives the same walks
+    walks2, alive2, _ = g.walk(start, nw, L, p, q, seed=4242, collect_stats=False)
+    assert n2v.torch.equal(walks, walks2) and n2v.torch.equal(alive, alive2)
+    if case[5] == 0.25 and not weighted:
+        assert consts.fold_mode == 1 and stats["fold_hits"] > 0
+    if p == 100.0:
+        assert stats["fallbacks"] > 0
+    if not sym:
+        assert stats["dead"] == int((~ra).sum())
+
+
+def _pair_counts(walks, pos):
+    out = {}
+    for row in walks:
+        key = (int(row[pos - 1]), int(row[pos]))
+        d = out.setdefault(key, {})
+        d[int(row[pos + 1])] = d.get(int(row[pos + 1]), 0) + 1
+    return out
+
+
+@pytest.mark.parametrize("p,q,weighted,sym", [(1.0, 1.0, True, False), (1.0, 0.5, False, True),
+                                              (0.25, 4.0, False, True), (4.0, 0.25, True, True),
+                                              (0.25, 4.0, True, False)])
+def test_walk_frequencies_match_reference_law(n2v, p, q, weighted, sym):
+    """chi-square (alpha = 1e-4) of device transition frequencies against the reference's
+    law, i.e. the normalised biased weights fed to generate_alias_tables."""
+    rng = np.random.default_rng(21)
+    src, dst, w = _random_arcs(rng, 14, 80, weighted, sym, False)
+    g = n2v.graph.DeviceGraph.from_arcs(src, dst, w if weighted else None, n_vertices=14)
+    adj = ref_walk.build_adjacency(src.tolist(), dst.tolist(), w.tolist())
+    start = g.start_vertices()
+    walks, alive, _ = g.walk(start, 20000, 3, p, q, seed=77)
+    walks = walks[alive].cpu().numpy()
+    for v in start.cpu().numpy()[:5]:
+        law = ref_walk.transition_law(adj, None, int(v), p, q)
+        rows = walks[walks[:, 0] == v]
+        ids = sorted(law)
+        ok, pval = chi_square_ok([(rows[:, 1] == x).sum() for x in ids], [law[x] for x in ids])
+        assert ok, (v, pval)
+    for pos in (1, 2):
+        table = _pair_counts(walks, pos)
+        for (t, v) in sorted(table, key=lambda k: -sum(table[k].values()))[:15]:
+            law = ref_walk.transition_law(adj, t, v, p, q)
+            ids = sorted(law)
+            assert set(table[(t, v)]) <= set(ids)
+            ok, pval = chi_square_ok([table[(t, v)].get(x, 0) for x in ids], [law[x] for x in ids])
+            assert ok, (t, v, pval)
+
+
+def test_walk_frequencies_match_reference_sampler_empirically(n2v):
+    """Same (t, v) pair, same graph: device frequencies vs frequencies of the REFERENCE's
+    sampler (oracle C port of next_step_random_walk, MT stream) -- two-sample chi-square."""
+    from scipy import stats as sst
+    rng = np.random.default_rng(8)
+    src, dst, w = _random_arcs(rng, 10, 50, True, False, False)
+    row_ptr, col, ws, _ = clib.csr_from_arcs(src, dst, w, 10)
+    g = n2v.graph.DeviceGraph.from_arcs(src, dst, w, n_vertices=10)
+    start = g.start_vertices().cpu().numpy()
+    gw, ga, _ = g.walk(start, 30000, 2, 0.5, 2.0, seed=5)
+    gw = gw[ga].cpu().numpy()
+    rw, ra = clib.reference_walk(row_ptr, col, ws, start, 30000, 2, 0.5, 2.0, "naive", None)
+    rw = rw[ra]
+    tg, tr = _pair_counts(gw, 1), _pair_counts(rw, 1)
+    for key in sorted(tg, key=lambda k: -sum(tg[k].values()))[:10]:
+        ids = sorted(set(tg[key]) | set(tr.get(key, {})))
+        a = np.array([tg[key].get(x, 0) for x in ids]); b = np.array([tr[key].get(x, 0) for x in ids])
+        keep = (a + b) >= 10
+        if keep.sum() < 2:
+            continue
+        _, pval, _, _ = sst.chi2_contingency(np.vstack([a[keep], b[keep]]))
+        assert pval > 1e-4, (key, pval)
+
+
+# ------------------------------------------------------------------ fugue-level facade
+def test_random_walk_facade_reference_graph(n2v):
+    """tests/test_fugue.py:58-76 of the reference, plus what it leaves unchecked."""
+    import pandas as pd
+    graph = [[0, 2, 0.41], [0, 4, 0.85], [3, 4, 0.36], [2, 0, 0.68], [4, 0, 0.1], [4, 3, 0.37]]
+    df = pd.DataFrame(graph, columns=["src", "dst", "weight"]).astype({"src": int, "dst": int})
+    params = {"num_walks": 2, "walk_length": 3, "return_param": 0.5}
+    res = n2v.fugue.random_walk(None, df, params, random_seed=3)
+    assert res is not None and params["inout_param"] == 1.0            # defaults merged in place
+    out = res.as_pandas()
+    assert list(out.columns) == ["src", "walk"] and len(out) == 4 * 2
+    arcs = {(a, b) for a, b, _ in graph}
+    for s, walk in zip(out["src"], out["walk"]):
+        assert len(walk) == 4 and walk[0] == s
+        assert all((a, b) in arcs for a, b in zip(walk[:-1], walk[1:]))
+    seeds = pd.DataFrame({"id": [0, 4, 99]})
+    res = n2v.fugue.random_walk(None, n2v.fugue.Frame(df), params, seeds, random_seed=3)
+    assert sorted(set(res.as_pandas()["src"])) == [0, 4] and res.count() == 4
+    with pytest.raises(ValueError):
+        n2v.fugue.random_walk(None, df, params, df)                     # walk_seed without "id"
+    with pytest.raises(ValueError):
+        n2v.fugue.random_walk(None, df, {"return_param": 0})
+    # determinism and seed sensitivity
+    a = n2v.fugue.random_walk(None, df, dict(params), random_seed=9).walks
+    b = n2v.fugue.random_walk(None, df, dict(params), random_seed=9).walks
+    c = n2v.fugue.random_walk(None, df, {"num_walks": 50, "walk_length": 8}, random_seed=10).walks
+    d = n2v.fugue.random_walk(None, df, {"num_walks": 50, "walk_length": 8}, random_seed=11).walks
+    assert np.array_equal(a, b) and not np.array_equal(c, d)
+
+
+def test_random_walk_drops_walkers_at_sinks(n2v):
+    import pandas as pd
+    fx = [r for r in load_golden("walks.json")["walks"] if r["graph"] == "sink_multi"][0]
+    df = pd.DataFrame({"src": fx["src"], "dst": fx["dst"], "weight": unhex(fx["weight"])})
+    res = n2v.fugue.random_walk(None, df, {"num_walks": 200, "walk_length": 5, "return_param": 2.0,
+                                           "inout_param": 0.5}, random_seed=1)
+    w = res.walks
+    assert 0 < len(w) < 4 * 200
+    has_out = set(fx["src"])
+    assert all(all(int(v) in has_out for v in row[:-1]) for row in w)   # only the last vertex may be a sink
+    assert (w >= 0).all()
+
+
+def test_trim_index_facade(n2v):
+    import pandas as pd
+    graph = [[0, 2, 0.41], [0, 4, 0.85], [3, 4, 0.36], [2, 0, 0.68], [4, 0, 0.1], [4, 3, 0.37]]
+    df = pd.DataFrame(graph, columns=["src", "dst", "weight"]).astype({"src": int, "dst": int})
+    r, name_id = n2v.fugue.trim_index(None, df, indexed=True)
+    assert len(r.as_pandas()) == 6 and name_id is None
+    r, name_id = n2v.fugue.trim_index(None, df, indexed=True, max_out_deg=1)
+    assert len(r.as_pandas()) == 4 and name_id is None
+    d1 = pd.DataFrame({"src": ["a1", "a1", "a1", "a2", "b2"], "dst": ["a2", "b1", "b2", "b1", "a2"]})
+    r, name_id = n2v.fugue.trim_index(None, d1, indexed=False)
+    assert len(r.as_pandas()) == 5 and len(name_id.as_pandas()) == 4
+    d2 = pd.DataFrame({"dst": ["a2", "b1", "b2", "a1"], "weight": [0.8, 1.1, 1.0, 0.3]})
+    with pytest.raises(ValueError):
+        n2v.fugue.trim_index(None, d2, False)
+    fx = load_golden("trim.json")
+    big = pd.DataFrame({"src": fx["src"], "dst": fx["dst"], "weight": unhex(fx["weight"])})
+    for c in fx["cases"]:
+        if c["random_seed"] is None and c["max_out_degree"] > 0:
+            continue
+        r, _ = n2v.fugue.trim_index(None, big, indexed=True, max_out_deg=c["max_out_degree"],
+                                    random_seed=c["random_seed"])
+        out = r.as_pandas()
+        assert out["src"].tolist() == c["src"] and out["dst"].tolist() == c["dst"]
+        assert [float(x).hex() for x in out["weight"]] == c["weight"]
+
+
+# ---------------------------------------------- BASELINE-size properties (configs[1] shape)
+def test_full_size_properties_config2(n2v):
+    """10k vertices / ~334k edges, p=0.25 q=4, 80 walks x 40: every hop is an arc, rows start
+    where they should, nothing dies on a symmetric graph, results are seed-deterministic."""
+    torch = n2v.torch
+    from node2vec_b200 import synth
+    src, dst = synth.blogcatalog_like(seed=42)
+    g = n2v.graph.DeviceGraph.from_arcs(src, dst, None, n_vertices=10000)
+    need = 1 | 2 | 4
+    assert g.flags & need == need
+    start = g.start_vertices()
+    walks, alive, stats = g.walk(start, 80, 40, 0.25, 4.0, seed=42, collect_stats=True)
+    assert bool(alive.all()) and walks.shape == (start.numel() * 80, 41)
+    assert torch.equal(walks[:, 0], start.repeat_interleave(80))
+    keys = (torch.as_tensor(src, device=walks.device).long() << 32) | torch.as_tensor(dst, device=walks.device).long()
+    keys = torch.sort(keys).values
+    hop = (walks[:, :-1].long() << 32) | walks[:, 1:].long()
+    pos = torch.searchsorted(keys, hop.reshape(-1)).clamp(max=keys.numel() - 1)
+    assert bool((keys[pos] == hop.reshape(-1)).all())
+    assert stats["steps"] == walks.shape[0] * 40 and stats["fallbacks"] == 0
+    w2, _, _ = g.walk(start, 80, 40, 0.25, 4.0, seed=42)
+    assert torch.equal(walks, w2)
+    sub, _, _ = g.walk(start[100:140], 80, 40, 0.25, 4.0, seed=42)      # sharding-invariant rows
+    assert torch.equal(sub, walks[100 * 80:140 * 80])
+    rw, ra, rs = _replay(g, 0.25, 4.0, start[:50].cpu().numpy(), 80, 40, 42)
+    assert np.array_equal(rw[:, :41], walks[:50 * 80].cpu().numpy())
