@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define N2V_ABI_VERSION 1
+#define N2V_ABI_VERSION 2
 #define N2V_MAX_PARTS 16
 
 /* error codes */
@@ -54,12 +54,30 @@ enum {
 };
 
 /* One vertex of the CSR: replaces one row of df_adj, i.e. one base64(pickle) adjacency
- * string (randomwalk.py:266-275, Neighbors :17-41).  16 B, loaded as one LDG.128. */
+ * string (randomwalk.py:266-275, Neighbors :17-41).  16 B, loaded as one LDG.128.
+ * Offsets are local to the vertex's part; a part holds fewer than 2^32 arcs. */
 typedef struct n2v_vertex {
-  uint64_t base; /* index of the first out-arc in arcs[] / col[] / weight[] */
-  uint32_t deg;  /* number of out-arcs */
-  float wsum;    /* (float) of the fp64 left-to-right sum of out-weights; used only by the weighted return-edge fold */
+  uint32_t base;  /* index of the first out-arc in arcs[] / col[] / weight[] */
+  uint32_t deg;   /* number of out-arcs */
+  uint32_t hbase; /* index of the first 32-byte bucket of this vertex's neighbour hash set in hash[] */
+  float wsum;     /* (float) of the fp64 left-to-right sum of out-weights (weighted return-edge fold) */
 } n2v_vertex_t;
+
+/* Neighbour hash set of a vertex: the membership test "x in N_out(t)" of
+ * generate_edge_alias_tables (randomwalk.py:226, a Python set) as ONE 32-byte gather.
+ * Vertex t owns n2v_hash_nbuckets(deg) consecutive buckets of 8 int32 slots (load <= 0.5),
+ * filled by linear probing over buckets in col[] order; empty slots hold N2V_HASH_EMPTY and
+ * a bucket's used slots are contiguous from slot 0.
+ *   bucket(x) = mulhi32(x * 0x9E3779B1, nbuckets) */
+#define N2V_HASH_SLOTS 8
+#define N2V_HASH_EMPTY (-1)
+#define N2V_HASH_MULT 0x9E3779B1u
+#ifdef __CUDACC__
+#define N2V_HD __host__ __device__
+#else
+#define N2V_HD
+#endif
+static inline N2V_HD uint32_t n2v_hash_nbuckets(uint32_t deg) { return (deg + 3u) >> 2; }
 
 /* One out-arc with its FIRST-ORDER alias-table entry folded in: replaces the
  * (alias[k], probs[k]) pair of generate_alias_tables (randomwalk.py:157-190) plus the
@@ -83,6 +101,7 @@ typedef struct n2v_graph_part {
   const n2v_arc_t* arcs;    /* [part arcs] */
   const int32_t* col;       /* [part arcs] neighbour ids, ascending within a vertex */
   const double* weight;     /* [part arcs] fp64 weights in col order */
+  const int32_t* hash;      /* [part buckets][8] neighbour hash sets */
 } n2v_graph_part_t;
 
 typedef struct n2v_graph {
@@ -99,8 +118,8 @@ typedef struct n2v_graph {
 typedef struct n2v_walk_stats {
   uint64_t steps;        /* walker-steps taken */
   uint64_t trials;       /* alias proposals drawn (>= steps; == steps when p == q == 1) */
-  uint64_t probes;       /* binary-search probes into N_out(prev) */
-  uint64_t searches;     /* membership tests that needed a search */
+  uint64_t probes;       /* 32-byte hash buckets read for membership tests (>= searches) */
+  uint64_t searches;     /* membership tests "x in N_out(prev)" the accept draw could not skip */
   uint64_t fold_hits;    /* steps resolved by the return-edge fold without a proposal */
   uint64_t fallbacks;    /* steps resolved by the exact O(deg) scan after N2V_MAX_TRIALS rejections */
   uint64_t dead;         /* walkers dropped at a vertex with no out-arcs (fugue.py:147 inner join) */
@@ -124,6 +143,17 @@ int n2v_csr_build(const int32_t* src, const int32_t* dst, const double* weight, 
                   int64_t n_vertices, n2v_vertex_t* vtx, int32_t* col, double* weight_sorted,
                   int64_t* perm, void* scratch, size_t scratch_bytes, uint32_t* flags_host,
                   void* stream);
+
+/* ---- K0b: neighbour hash sets -----------------------------------------------------
+ * Replaces `set(Neighbors(src_nbs).dst_id)` (randomwalk.py:318), built once per vertex
+ * instead of once per walker per step.  hash: [n_buckets_cap][8] int32 with
+ * n_buckets_cap >= n2v_hash_buckets_bound(); fills vtx[].hbase; *n_buckets_host = buckets
+ * used (synchronises the stream to return it). */
+int64_t n2v_hash_buckets_bound(int64_t n_arcs, int64_t n_vertices);
+size_t n2v_hash_scratch_bytes(int64_t n_vertices);
+int n2v_hash_build(n2v_vertex_t* vtx, const int32_t* col, int64_t n_vertices, int64_t n_arcs,
+                   int32_t* hash, int64_t n_buckets_cap, void* scratch, size_t scratch_bytes,
+                   int64_t* n_buckets_host, void* stream);
 
 /* ---- K1: per-vertex first-order alias tables, bit-exact fp64 ------------------------
  * Replaces generate_alias_tables (randomwalk.py:157-190) for every vertex at once (the

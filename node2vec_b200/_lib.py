@@ -15,7 +15,8 @@ GRAPH_UNIT_WEIGHT, GRAPH_SYMMETRIC, GRAPH_SIMPLE = 1, 2, 4
 
 
 class GraphPart(C.Structure):
-    _fields_ = [("vtx", C.c_void_p), ("arcs", C.c_void_p), ("col", C.c_void_p), ("weight", C.c_void_p)]
+    _fields_ = [("vtx", C.c_void_p), ("arcs", C.c_void_p), ("col", C.c_void_p), ("weight", C.c_void_p),
+                ("hash", C.c_void_p)]
 
 
 class Graph(C.Structure):
@@ -38,6 +39,10 @@ _SIGNATURES = {
     "n2v_csr_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "n2v_csr_build": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t,
                                 C.POINTER(C.c_uint32), _P]),
+    "n2v_hash_buckets_bound": (C.c_int64, [C.c_int64, C.c_int64]),
+    "n2v_hash_scratch_bytes": (C.c_size_t, [C.c_int64]),
+    "n2v_hash_build": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, C.c_int64, _P, C.c_size_t,
+                                 C.POINTER(C.c_int64), _P]),
     "n2v_alias_build": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P, _P, _P,
                                   C.POINTER(C.c_int64), _P]),
     "n2v_edge_alias_build": (C.c_int, [C.POINTER(Graph), _P, _P, C.c_int64, C.c_double, C.c_double, C.c_int,
@@ -64,11 +69,12 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_build.SO):
-        if not build_if_missing:
-            raise N2VError(f"{_build.SO} is missing: run `python -m node2vec_b200.build`")
+    path = os.environ.get("N2V_B200_LIB", _build.SO)   # override = kernel-tuning builds only
+    if not os.path.exists(path):
+        if not build_if_missing or path != _build.SO:
+            raise N2VError(f"{path} is missing: run `python -m node2vec_b200.build`")
         _build.build_library()
-    lib = C.CDLL(_build.SO)
+    lib = C.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = ABI mismatch, loudly
         fn.restype = res

@@ -47,7 +47,7 @@ __global__ void scatter_sorted(const uint64_t* __restrict__ keys, const uint32_t
     if (i > 0) {
       const uint64_t kp = keys[i - 1];
       if (kp == k) local |= N2V_GRAPH_SIMPLE;
-      if (static_cast<uint32_t>(kp >> 32) != s) vtx[s].base = static_cast<uint64_t>(i);
+      if (static_cast<uint32_t>(kp >> 32) != s) vtx[s].base = static_cast<uint32_t>(i);
     } else {
       vtx[s].base = 0;
     }
@@ -60,7 +60,7 @@ __global__ void close_runs(const uint64_t* __restrict__ keys, int64_t n, n2v_ver
   for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) {
     const uint32_t s = static_cast<uint32_t>(keys[i] >> 32);
     if (i + 1 == n || static_cast<uint32_t>(keys[i + 1] >> 32) != s)
-      vtx[s].deg = static_cast<uint32_t>(i + 1 - vtx[s].base);
+      vtx[s].deg = static_cast<uint32_t>(i + 1) - vtx[s].base;
   }
 }
 

@@ -33,19 +33,9 @@ void set_error(const char* fmt, ...);
 constexpr int kSmCount = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
 // ---- 16-byte record loads (one LDG.128 each, read-only path) ------------------------
-struct VtxRec {
-  uint64_t base;
-  uint32_t deg;
-  float wsum;
-};
-
-__device__ __forceinline__ VtxRec load_vtx(const n2v_vertex_t* p) {
-  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
-  VtxRec r;
-  r.base = (static_cast<uint64_t>(q.y) << 32) | q.x;
-  r.deg = q.z;
-  r.wsum = __uint_as_float(q.w);
-  return r;
+// {base, deg, hbase, wsum-bits} of a vertex in one load
+__device__ __forceinline__ uint4 load_vtx(const n2v_vertex_t* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
 }
 
 __device__ __forceinline__ int4 load_arc(const n2v_arc_t* p) {

@@ -4,18 +4,19 @@
 //   initiate_random_walk                      (randomwalk.py:279-296)
 //   [left join on src, inner join on dst]     (fugue.py:147)
 //   next_step_random_walk  x walk_length      (randomwalk.py:300-339), which per row
-//       unpickles two adjacency strings, rebuilds an O(deg) alias table
-//       (generate_edge_alias_tables :193-232) and draws once (:86-99)
+//       unpickles two adjacency strings, builds a Python set of N_out(prev), rebuilds an
+//       O(deg) alias table (generate_edge_alias_tables :193-232) and draws once (:86-99)
 //   to_path                                   (randomwalk.py:343-349)
 //
 // Sampling.  The reference's law for the next vertex x, given the previous vertex t and
 // the current vertex v, is  P(x) ~ w(v,x) * alpha(t,x)  with alpha = 1/p (x == t),
 // 1 (x in N_out(t)), 1/q (otherwise) (randomwalk.py:223-230).  We draw from exactly that
 // law without building the per-(t,v) table: propose x from v's FIRST-ORDER alias table
-// (one 16-byte gather), accept with alpha/cap; membership in N_out(t) is a binary search
-// of t's sorted neighbour slice and is skipped whenever the accept draw already decides
-// (u below both thresholds / above both).  The return arc's excess mass (1/p above cap)
-// is a separate mixture component (the "fold"), so small p does not inflate the envelope.
+// (one 16-byte gather), accept with alpha/cap; membership in N_out(t) is one 32-byte
+// gather from t's bucketed hash set and is skipped whenever the accept draw already
+// decides (u below both thresholds / above both).  The return arc's excess mass (1/p above
+// cap) is a separate mixture component (the "fold"), so small p does not inflate the
+// envelope.
 //
 // Execution model.  One thread per walker, lanes fully asynchronous: the loop body is ONE
 // proposal; a lane whose proposal is accepted advances its own step counter, a lane that
@@ -25,7 +26,7 @@
 //
 // Determinism.  Philox4x32-10, key = seed, counter = (walk_id lo, walk_id hi, step,
 // trial); all sampling decisions are integer compares, the fold threshold is three IEEE
-// fp32 ops.  oracle/csrc/walk_replay.c restates this on the host bit-for-bit.
+// fp32 ops.  oracle/csrc/n2v_oracle.c (orc_replay_walk) restates this on the host bit-for-bit.
 #include "n2v_internal.cuh"
 
 namespace {
@@ -39,15 +40,15 @@ constexpr int kStage = 8;  // ids per lane per flush = one 32 B sector
 
 struct WalkArgs {
   const int32_t* start;
-  int64_t n_start;
-  int64_t n_walkers;
+  int32_t* walks;
+  uint8_t* alive;
+  unsigned long long* stats;
+  int64_t pitch;
+  uint32_t n_walkers;  // per launch (< 2^31; the host chunks larger jobs)
+  uint32_t walker0;    // global index of this launch's first walker
   int32_t num_walks;
   int32_t walk_length;
   uint32_t key0, key1;
-  int32_t* walks;
-  int64_t pitch;
-  uint8_t* alive;
-  unsigned long long* stats;
   // accept iff u32 <= *_m1
   uint32_t ret_m1, nbr_m1, far_m1, lo_m1, hi_m1;
   float fold_gain;
@@ -55,38 +56,30 @@ struct WalkArgs {
   double inv_p, inv_q;
 };
 
-struct Part {
-  const n2v_vertex_t* vtx;
-  const n2v_arc_t* arcs;
-  const int32_t* col;
-  const double* weight;
-};
-
-template <bool MULTI>
-__device__ __forceinline__ Part part_of(const n2v_graph_t& g, int32_t v, int32_t& local) {
-  if (MULTI) {
-    const int32_t pi = static_cast<int32_t>(v / g.part_size);
-    local = v - static_cast<int32_t>(pi * g.part_size);
-    const n2v_graph_part_t& p = g.parts[pi];
-    return Part{p.vtx, p.arcs, p.col, p.weight};
+// x in N_out(t)?  t's hash set: nb buckets of 8 slots starting at bucket hbase
+__device__ __forceinline__ bool member(const int32_t* __restrict__ hash, uint32_t hbase, uint32_t deg,
+                                       int32_t x, uint32_t& probes) {
+  const uint32_t nb = n2v_hash_nbuckets(deg);
+  uint32_t b = __umulhi(static_cast<uint32_t>(x) * N2V_HASH_MULT, nb);
+  for (;;) {
+    const int4* p = reinterpret_cast<const int4*>(hash + (static_cast<size_t>(hbase) + b) * N2V_HASH_SLOTS);
+    const int4 lo = __ldg(p), hi = __ldg(p + 1);
+    ++probes;
+    if (lo.x == x || lo.y == x || lo.z == x || lo.w == x || hi.x == x || hi.y == x || hi.z == x || hi.w == x)
+      return true;
+    if (hi.w == N2V_HASH_EMPTY) return false;  // bucket not full: x would have been here
+    b = (b + 1 == nb) ? 0u : b + 1;
   }
-  local = v;
-  const n2v_graph_part_t& p = g.parts[0];
-  return Part{p.vtx, p.arcs, p.col, p.weight};
 }
 
-// lower_bound membership test in an ascending slice; counts probes
-__device__ __forceinline__ bool member(const int32_t* __restrict__ col, uint32_t n, int32_t x,
-                                       uint32_t& probes) {
+// lower_bound membership in an ascending slice (cold path: exact fallback only)
+__device__ bool member_sorted(const int32_t* __restrict__ col, uint32_t n, int32_t x) {
   uint32_t lo = 0, hi = n;
   while (lo < hi) {
     const uint32_t mid = (lo + hi) >> 1;
-    ++probes;
-    if (__ldg(col + mid) < x) lo = mid + 1; else hi = mid;
+    if (col[mid] < x) lo = mid + 1; else hi = mid;
   }
-  if (lo >= n) return false;
-  ++probes;
-  return __ldg(col + lo) == x;
+  return lo < n && col[lo] == x;
 }
 
 // Exact O(deg log deg) draw from the biased law; used only after max_trials rejections so
@@ -94,11 +87,11 @@ __device__ __forceinline__ bool member(const int32_t* __restrict__ col, uint32_t
 __device__ __noinline__ int32_t exact_draw(const int32_t* __restrict__ vcol, const double* __restrict__ vw,
                                            uint32_t deg, int32_t t, const int32_t* __restrict__ tcol,
                                            uint32_t tdeg, double inv_p, double inv_q, uint32_t r0,
-                                           uint32_t r1, uint32_t& probes) {
+                                           uint32_t r1) {
   double total = 0.0;
   for (uint32_t i = 0; i < deg; ++i) {
     const int32_t x = vcol[i];
-    const double a = (x == t) ? inv_p : (member(tcol, tdeg, x, probes) ? 1.0 : inv_q);
+    const double a = (x == t) ? inv_p : (member_sorted(tcol, tdeg, x) ? 1.0 : inv_q);
     total = __dadd_rn(total, __dmul_rn(vw[i], a));
   }
   // 53-bit uniform in [0,1) from two 32-bit lanes
@@ -110,7 +103,7 @@ __device__ __noinline__ int32_t exact_draw(const int32_t* __restrict__ vcol, con
   int32_t last = vcol[deg - 1];
   for (uint32_t i = 0; i < deg; ++i) {
     const int32_t x = vcol[i];
-    const double a = (x == t) ? inv_p : (member(tcol, tdeg, x, probes) ? 1.0 : inv_q);
+    const double a = (x == t) ? inv_p : (member_sorted(tcol, tdeg, x) ? 1.0 : inv_q);
     const double m = __dmul_rn(vw[i], a);
     run = __dadd_rn(run, m);
     if (m > 0.0) last = x;
@@ -129,30 +122,32 @@ template <bool FOLD, bool MULTI, bool STATS>
 __global__ void __launch_bounds__(kBlock, kBlocksPerSm)
 walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkArgs A) {
   __shared__ int32_t stage[kStage * kBlock];  // [slot][thread]: conflict-free
-  const int tid = threadIdx.x;
-  const int64_t stride = int64_t(gridDim.x) * kBlock;
-  int64_t w = blockIdx.x * int64_t(kBlock) + tid;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t stride = gridDim.x * kBlock;
+  uint32_t w = blockIdx.x * kBlock + tid;
 
   uint32_t c_steps = 0, c_trials = 0, c_probes = 0, c_search = 0, c_fold = 0, c_fb = 0, c_dead = 0;
 
-  // walker state
+  // walker state (offsets are 32-bit: a part holds < 2^32 arcs / buckets)
   int32_t t = -1, v = 0, pos = 0;
-  uint32_t deg_t = 0, deg_v = 0, trial = 0, thr_out = 0;
-  uint64_t base_v = 0, walk_id = 0;
-  Part pv{};
-  const int32_t* tcol = nullptr;
+  uint32_t deg_t = 0, deg_v = 0, base_v = 0, base_t = 0, hbase_v = 0, hbase_t = 0;
+  uint32_t trial = 0, thr_out = 0, wid_lo = 0, wid_hi = 0;
+  uint32_t part_v = 0, part_t = 0;
   bool active = false;
   const int32_t L = A.walk_length;
 
+  auto row_ptr = [&](int chunk) {
+    return reinterpret_cast<int4*>(A.walks + static_cast<int64_t>(w) * A.pitch + chunk * kStage);
+  };
   auto flush_chunk = [&](int chunk) {
     int4 a, b;
     a.x = stage[0 * kBlock + tid]; a.y = stage[1 * kBlock + tid];
     a.z = stage[2 * kBlock + tid]; a.w = stage[3 * kBlock + tid];
     b.x = stage[4 * kBlock + tid]; b.y = stage[5 * kBlock + tid];
     b.z = stage[6 * kBlock + tid]; b.w = stage[7 * kBlock + tid];
-    int4* dst = reinterpret_cast<int4*>(A.walks + w * A.pitch + int64_t(chunk) * kStage);
-    dst[0] = a;
-    dst[1] = b;
+    int4* dst = row_ptr(chunk);
+    __stcs(dst, a);       // streaming: the walk matrix is write-once
+    __stcs(dst + 1, b);
   };
   // end of a walk (complete or dropped): pad the row with -1 and release the lane
   auto finish = [&](bool is_alive) {
@@ -161,27 +156,38 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
     flush_chunk(chunk);
     const int4 neg = make_int4(-1, -1, -1, -1);
     for (++chunk; chunk * kStage < A.pitch; ++chunk) {
-      int4* dst = reinterpret_cast<int4*>(A.walks + w * A.pitch + int64_t(chunk) * kStage);
-      dst[0] = neg;
-      dst[1] = neg;
+      int4* dst = row_ptr(chunk);
+      __stcs(dst, neg);
+      __stcs(dst + 1, neg);
     }
     A.alive[w] = is_alive ? 1 : 0;
     active = false;
     w += stride;
   };
+  auto enter = [&](int32_t x, uint32_t& part, uint32_t& base, uint32_t& deg, uint32_t& hbase) {
+    uint32_t local = static_cast<uint32_t>(x);
+    part = 0;
+    if (MULTI) {
+      part = static_cast<uint32_t>(x / g.part_size);
+      local = static_cast<uint32_t>(x - part * g.part_size);
+    }
+    const uint4 rec = n2v::load_vtx(g.parts[part].vtx + local);
+    base = rec.x;
+    deg = rec.y;
+    hbase = rec.z;
+  };
 
   for (;;) {
     if (!active) {
       if (w >= A.n_walkers) break;
-      const int64_t s = w / A.num_walks;
-      const int32_t r = static_cast<int32_t>(w - s * A.num_walks);
+      const uint32_t gw = A.walker0 + w;
+      const uint32_t s = gw / static_cast<uint32_t>(A.num_walks);
+      const uint32_t r = gw - s * static_cast<uint32_t>(A.num_walks);
       v = __ldg(A.start + s);
-      walk_id = static_cast<uint64_t>(static_cast<uint32_t>(v)) * static_cast<uint32_t>(A.num_walks) + r;
-      int32_t local;
-      pv = part_of<MULTI>(g, v, local);
-      const n2v::VtxRec rec = n2v::load_vtx(pv.vtx + local);
-      base_v = rec.base;
-      deg_v = rec.deg;
+      const uint64_t walk_id = static_cast<uint64_t>(static_cast<uint32_t>(v)) * static_cast<uint32_t>(A.num_walks) + r;
+      wid_lo = static_cast<uint32_t>(walk_id);
+      wid_hi = static_cast<uint32_t>(walk_id >> 32);
+      enter(v, part_v, base_v, deg_v, hbase_v);
       t = -1;
       pos = 0;
       trial = 0;
@@ -193,9 +199,7 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
       finish(false);
       continue;
     }
-    const uint4 rnd = n2v::philox4x32_10(A.key0, A.key1, static_cast<uint32_t>(walk_id),
-                                         static_cast<uint32_t>(walk_id >> 32),
-                                         static_cast<uint32_t>(pos), trial);
+    const uint4 rnd = n2v::philox4x32_10(A.key0, A.key1, wid_lo, wid_hi, static_cast<uint32_t>(pos), trial);
     const bool first = (pos == 0);
     bool accept;
     int32_t x;
@@ -205,37 +209,38 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
       if (STATS) ++c_fold;
     } else {
       const uint32_t k = __umulhi(rnd.y, deg_v);
-      const int4 arc = n2v::load_arc(pv.arcs + base_v + k);
+      const int4 arc = n2v::load_arc(g.parts[MULTI ? part_v : 0].arcs + base_v + k);
       x = (rnd.z < static_cast<uint32_t>(arc.x)) ? arc.y : arc.z;
       if (STATS) ++c_trials;
       if (first) accept = true;                       // unbiased first step (randomwalk.py:320-321)
       else if (x == t) accept = rnd.w <= A.ret_m1;
-      else if (rnd.w <= A.lo_m1) accept = true;       // below both thresholds: no search needed
+      else if (rnd.w <= A.lo_m1) accept = true;       // below both thresholds: no lookup needed
       else if (rnd.w > A.hi_m1) accept = false;       // above both
       else {
         if (STATS) ++c_search;
-        accept = rnd.w <= (member(tcol, deg_t, x, c_probes) ? A.nbr_m1 : A.far_m1);
+        uint32_t probes = 0;
+        const bool in = member(g.parts[MULTI ? part_t : 0].hash, hbase_t, deg_t, x, probes);
+        if (STATS) c_probes += probes;
+        accept = rnd.w <= (in ? A.nbr_m1 : A.far_m1);
       }
     }
     if (!accept) {
       if (++trial < static_cast<uint32_t>(A.max_trials)) continue;
-      const uint4 r2 = n2v::philox4x32_10(A.key0, A.key1, static_cast<uint32_t>(walk_id),
-                                          static_cast<uint32_t>(walk_id >> 32),
-                                          static_cast<uint32_t>(pos), 0xFFFFFFFFu);
-      x = exact_draw(pv.col + base_v, pv.weight + base_v, deg_v, t, tcol, deg_t, A.inv_p, A.inv_q,
-                     r2.x, r2.y, c_probes);
+      const uint4 r2 = n2v::philox4x32_10(A.key0, A.key1, wid_lo, wid_hi, static_cast<uint32_t>(pos), 0xFFFFFFFFu);
+      const n2v_graph_part_t& PV = g.parts[MULTI ? part_v : 0];
+      const n2v_graph_part_t& PT = g.parts[MULTI ? part_t : 0];
+      x = exact_draw(PV.col + base_v, PV.weight + base_v, deg_v, t, PT.col + base_t, deg_t, A.inv_p, A.inv_q,
+                     r2.x, r2.y);
       if (STATS) ++c_fb;
     }
     // advance: v becomes the previous vertex
     t = v;
-    tcol = pv.col + base_v;
+    base_t = base_v;
     deg_t = deg_v;
+    hbase_t = hbase_v;
+    part_t = part_v;
     v = x;
-    int32_t local;
-    pv = part_of<MULTI>(g, v, local);
-    const n2v::VtxRec rec = n2v::load_vtx(pv.vtx + local);
-    base_v = rec.base;
-    deg_v = rec.deg;
+    enter(v, part_v, base_v, deg_v, hbase_v);
     ++pos;
     if (STATS) ++c_steps;
     trial = 0;
@@ -248,9 +253,8 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
     if (FOLD) thr_out = fold_threshold(A.fold_gain, deg_v);
   }
 
-  // one atomic per counter per warp
-  unsigned long long vals[7] = {c_steps, c_trials, c_probes, c_search, c_fold, c_fb, c_dead};
-  if (STATS) {
+  if (STATS) {  // one atomic per counter per warp
+    unsigned long long vals[7] = {c_steps, c_trials, c_probes, c_search, c_fold, c_fb, c_dead};
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
       unsigned long long x = vals[i];
@@ -280,18 +284,17 @@ extern "C" int n2v_walk(const n2v_graph_t* graph, const int32_t* start, int64_t 
   if (n_start == 0) return N2V_OK;
   N2V_CHECK_ARG(start && walks && alive, "n2v_walk: NULL buffer");
   N2V_CHECK_ARG((reinterpret_cast<uintptr_t>(walks) & 31) == 0, "n2v_walk: walks must be 32-byte aligned");
+  const int64_t total = n_start * num_walks;
+  N2V_CHECK_ARG(total < (int64_t(1) << 32), "n2v_walk: %lld walkers per call exceed 2^32; shard the start list",
+                static_cast<long long>(total));
 
   WalkArgs A{};
   A.start = start;
-  A.n_start = n_start;
-  A.n_walkers = n_start * num_walks;
   A.num_walks = num_walks;
   A.walk_length = walk_length;
   A.key0 = static_cast<uint32_t>(seed);
   A.key1 = static_cast<uint32_t>(seed >> 32);
-  A.walks = walks;
   A.pitch = pitch;
-  A.alive = alive;
   A.stats = reinterpret_cast<unsigned long long*>(stats);
   A.ret_m1 = static_cast<uint32_t>(C.t_ret - 1);
   A.nbr_m1 = static_cast<uint32_t>(C.t_nbr - 1);
@@ -303,24 +306,32 @@ extern "C" int n2v_walk(const n2v_graph_t* graph, const int32_t* start, int64_t 
   A.inv_p = 1.0 / return_param;
   A.inv_q = 1.0 / inout_param;
 
-  const int64_t need = (A.n_walkers + kBlock - 1) / kBlock;
-  const int64_t cap = int64_t(n2v::kSmCount) * kBlocksPerSm;
-  const int grid = static_cast<int>(need < cap ? need : cap);
   const bool fold = C.fold_mode != 0;
   const bool multi = graph->n_parts > 1;
   const bool st = stats != nullptr;
+  const int64_t chunk_max = int64_t(1) << 30;  // walkers per launch
+  for (int64_t w0 = 0; w0 < total; w0 += chunk_max) {
+    const int64_t n = total - w0 < chunk_max ? total - w0 : chunk_max;
+    A.walker0 = static_cast<uint32_t>(w0);
+    A.n_walkers = static_cast<uint32_t>(n);
+    A.walks = walks + w0 * pitch;
+    A.alive = alive + w0;
+    const int64_t need = (n + kBlock - 1) / kBlock;
+    const int64_t cap = int64_t(n2v::kSmCount) * kBlocksPerSm;
+    const int grid = static_cast<int>(need < cap ? need : cap);
 #define N2V_LAUNCH_WALK(F, M, S) walk_kernel<F, M, S><<<grid, kBlock, 0, stream>>>(*graph, A)
-  switch ((fold ? 4 : 0) | (multi ? 2 : 0) | (st ? 1 : 0)) {
-    case 0: N2V_LAUNCH_WALK(false, false, false); break;
-    case 1: N2V_LAUNCH_WALK(false, false, true); break;
-    case 2: N2V_LAUNCH_WALK(false, true, false); break;
-    case 3: N2V_LAUNCH_WALK(false, true, true); break;
-    case 4: N2V_LAUNCH_WALK(true, false, false); break;
-    case 5: N2V_LAUNCH_WALK(true, false, true); break;
-    case 6: N2V_LAUNCH_WALK(true, true, false); break;
-    default: N2V_LAUNCH_WALK(true, true, true); break;
-  }
+    switch ((fold ? 4 : 0) | (multi ? 2 : 0) | (st ? 1 : 0)) {
+      case 0: N2V_LAUNCH_WALK(false, false, false); break;
+      case 1: N2V_LAUNCH_WALK(false, false, true); break;
+      case 2: N2V_LAUNCH_WALK(false, true, false); break;
+      case 3: N2V_LAUNCH_WALK(false, true, true); break;
+      case 4: N2V_LAUNCH_WALK(true, false, false); break;
+      case 5: N2V_LAUNCH_WALK(true, false, true); break;
+      case 6: N2V_LAUNCH_WALK(true, true, false); break;
+      default: N2V_LAUNCH_WALK(true, true, true); break;
+    }
 #undef N2V_LAUNCH_WALK
-  N2V_LAUNCH_OK();
+    N2V_LAUNCH_OK();
+  }
   return N2V_OK;
 }

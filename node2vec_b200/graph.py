@@ -31,9 +31,10 @@ class DeviceGraph:
     """Sorted CSR + alias records in HBM.
 
     Layout (one replica):
-      vtx   int32[V, 4]   16 B/vertex  {base u64, deg u32, wsum f32}
+      vtx   int32[V, 4]   16 B/vertex  {base u32, deg u32, hbase u32, wsum f32}
       arcs  int32[A, 4]   16 B/arc     {thr u32, dst i32, alias_dst i32, alias_idx i32}
-      col   int32[A]       4 B/arc     neighbour ids, ascending per vertex (membership search)
+      hash  int32[B, 8]   ~8 B/arc     per-vertex neighbour hash sets, 32 B buckets (membership test)
+      col   int32[A]       4 B/arc     neighbour ids, ascending per vertex (exact fallback, parity)
       weight f64[A]        8 B/arc     reference weights (exact fallback, parity outputs)
     ``alias`` / ``probs`` (the reference's tables, bit-exact) are kept only on request.
     """
@@ -42,7 +43,7 @@ class DeviceGraph:
         self.n_vertices = 0
         self.n_arcs = 0
         self.flags = 0
-        self.vtx = self.arcs = self.col = self.weight = None
+        self.vtx = self.arcs = self.col = self.weight = self.hash = None
         self.alias = self.probs = self.perm = None
         self.device = None
         self.sum_mode = "naive"
@@ -84,6 +85,16 @@ class DeviceGraph:
                                          _lib.ptr(scratch), nbytes, C.byref(flags), stream), "n2v_csr_build")
             g.flags = int(flags.value)
             del scratch, s, d, w
+            n_buckets = int(lib.n2v_hash_buckets_bound(n_arcs, g.n_vertices))
+            g.hash = torch.empty((n_buckets, 8), dtype=torch.int32, device=device)
+            hbytes = int(lib.n2v_hash_scratch_bytes(g.n_vertices))
+            hscratch = torch.empty(hbytes, dtype=torch.uint8, device=device)
+            used = C.c_int64(0)
+            _lib.check(lib.n2v_hash_build(_lib.ptr(g.vtx), _lib.ptr(g.col), g.n_vertices, n_arcs, _lib.ptr(g.hash),
+                                          n_buckets, _lib.ptr(hscratch), hbytes, C.byref(used), stream),
+                       "n2v_hash_build")
+            g.n_buckets = int(used.value)
+            del hscratch
             g.arcs = torch.empty((n_arcs, 4), dtype=torch.int32, device=device)
             probs = torch.empty(n_arcs, dtype=torch.float64, device=device)
             alias = torch.empty(n_arcs, dtype=torch.int32, device=device) if keep_tables else None
@@ -106,6 +117,7 @@ class DeviceGraph:
         st.parts[0].arcs = self.arcs.data_ptr()
         st.parts[0].col = self.col.data_ptr()
         st.parts[0].weight = self.weight.data_ptr()
+        st.parts[0].hash = self.hash.data_ptr()
         self._struct = st
 
     # ------------------------------------------------------------------ views
@@ -114,27 +126,26 @@ class DeviceGraph:
         return self._struct
 
     def degrees(self) -> torch.Tensor:
-        return self.vtx[:, 2].clone()
-
-    def bases(self) -> torch.Tensor:
-        return self.vtx[:, :2].contiguous().view(torch.int64).view(-1)
+        return self.vtx[:, 1].clone()
 
     def start_vertices(self) -> torch.Tensor:
         """Vertices with at least one out-arc, ascending -- ``walk_start = df_adj[["id"]]``
         (fugue.py:132): only they start walks."""
-        return torch.nonzero(self.vtx[:, 2] != 0).view(-1).to(torch.int32)
+        return torch.nonzero(self.vtx[:, 1] != 0).view(-1).to(torch.int32)
 
     def nbytes(self) -> int:
-        return sum(int(t.numel()) * t.element_size() for t in (self.vtx, self.arcs, self.col, self.weight))
+        return sum(int(t.numel()) * t.element_size() for t in (self.vtx, self.arcs, self.col, self.weight, self.hash))
 
     def to_host(self) -> Dict[str, np.ndarray]:
         """Plain host arrays (for tests and the oracle's replay)."""
         vtx = self.vtx.cpu().numpy()
         arcs = self.arcs.cpu().numpy()
         out = {
-            "base": vtx[:, :2].copy().view(np.uint64).reshape(-1),
-            "deg": vtx[:, 2].copy().view(np.uint32),
+            "base": vtx[:, 0].copy().view(np.uint32).astype(np.uint64),
+            "deg": vtx[:, 1].copy().view(np.uint32),
+            "hbase": vtx[:, 2].copy().view(np.uint32),
             "wsum": vtx[:, 3].copy().view(np.float32),
+            "hash": self.hash.cpu().numpy()[: getattr(self, "n_buckets", 0)],
             "thr": arcs[:, 0].copy().view(np.uint32),
             "dst": arcs[:, 1].copy(),
             "alias_dst": arcs[:, 2].copy(),

