@@ -218,6 +218,74 @@ typedef struct n2v_walk_consts {
 int n2v_walk_consts(double return_param, double inout_param, uint32_t graph_flags,
                     n2v_walk_consts_t* out_host);
 
+
+/* ================================ SGNS half ========================================
+ * Replaces gensim.models.Word2Vec(sentences=all_walks, sg=1, negative=K, ...) as called by
+ * Node2VecGensim.fit (embedding.py:120-127): vocabulary statistics, sub-sampling
+ * thresholds, negative-sampling table, weight init and the skip-gram negative-sampling
+ * SGD itself.  Tokens are vertex ids and index the embedding tables directly (row v of
+ * syn0 / syn1neg belongs to vertex v); ids whose count is below min_count never occur in a
+ * training sentence, exactly like gensim's out-of-vocabulary words. */
+
+/* K4a: per-id token count and first flat position (row * len + column) over a walk matrix
+ * walks[n_walks][pitch] (first `len` columns valid, negative entries ignored).
+ * counts / first_pos: [n_vertices] int64, ACCUMULATED / MIN-ed into (caller initialises:
+ * counts = 0, first_pos = INT64_MAX); pos_offset is added to positions (multi-shard). */
+int n2v_vocab_count(const int32_t* walks, int64_t n_walks, int32_t len, int64_t pitch,
+                    int64_t n_vertices, int64_t pos_offset, int64_t* counts, int64_t* first_pos,
+                    void* stream);
+
+/* K4b: gensim prepare_vocab / make_cum_table from counts.
+ *   keep_thr[v]  : token v survives sub-sampling iff u32 < keep_thr[v] or keep_thr[v] == 2^32-1;
+ *                  0 for ids with count < min_count (dropped from every sentence)
+ *   neg_table[v] : {thr u32, alias i32} alias table over ids, P(v) ~ count^ns_exponent
+ *                  (0 for dropped ids): one 8-byte gather per negative
+ * scratch: n_vertices * 12 bytes (fp64 probs + int32 work list).
+ * totals_host[0] = retained token total, [1] = retained ids.  Synchronises the stream. */
+int n2v_sgns_prepare(const int64_t* counts, int64_t n_vertices, int64_t min_count, double sample,
+                     double ns_exponent, uint32_t* keep_thr, int32_t* neg_table, void* scratch,
+                     int64_t* totals_host, void* stream);
+
+/* weight init: syn0[v][d] = (U[0,1) - 0.5) / dim from Philox(seed; v, d/4) -- gensim's
+ * reset_weights law; syn1neg is the caller's zero-filled buffer. */
+int n2v_sgns_init(float* syn0, int64_t n_vertices, int32_t dim, uint64_t seed, void* stream);
+
+/* the 1000-entry sigmoid table of word2vec (EXP_TABLE), host pointer out[1000] */
+int n2v_sgns_exp_table(float* out_host);
+
+typedef struct n2v_sgns_params {
+  int32_t dim;          /* embedding width; multiple of 4, <= 1024 */
+  int32_t window;       /* gensim `window` */
+  int32_t negative;     /* gensim `negative` (K >= 1) */
+  int32_t epochs;       /* gensim `iter`: total epochs of the schedule */
+  int32_t epoch;        /* epoch this call runs (0-based) */
+  int32_t batch_words;  /* gensim `batch_words`: alpha is refreshed per job of this many words */
+  int32_t atomic_updates; /* 1 = red.global.add row updates, 0 = plain Hogwild stores like gensim */
+  int32_t reserved;
+  float alpha;          /* gensim `alpha` */
+  float min_alpha;      /* gensim `min_alpha` */
+  uint64_t seed;
+  int64_t walk_offset;  /* global index of this shard's first walk (schedule + RNG streams) */
+  int64_t total_walks;  /* walks per epoch over all shards */
+} n2v_sgns_params_t;
+
+/* K3: one epoch of skip-gram negative sampling over walks[n_walks][pitch] (`len` tokens each).
+ * One warp per walk: sub-sample, then for every centre i draw the reduced window and for every
+ * context j update (syn0[walk[j]], syn1neg[walk[i]], syn1neg[K negatives]).
+ * stats (device, 4 x uint64, accumulated): [0] pairs trained, [1] tokens kept, [2] negatives
+ * skipped (== centre), [3] targets skipped by the |f| >= 6 clip.
+ * trace (device int32[trace_cap][2 + negative], may be NULL): when given, ONE warp runs the
+ * walks in order and records every pair {centre, context, negatives (-1 = skipped)} and its
+ * alpha in trace_alpha; pairs beyond trace_cap are trained but not recorded. */
+int n2v_sgns_train(const int32_t* walks, int64_t n_walks, int32_t len, int64_t pitch,
+                   const uint32_t* keep_thr, const int32_t* neg_table, int64_t n_vertices,
+                   float* syn0, float* syn1neg, const float* exp_table, const n2v_sgns_params_t* params,
+                   uint64_t* stats, int32_t* trace, float* trace_alpha, int64_t trace_cap,
+                   void* stream);
+
+/* x[i] *= factor (the 1/G of model averaging after an NCCL sum-allreduce) */
+int n2v_scale(float* x, int64_t n, float factor, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

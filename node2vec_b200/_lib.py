@@ -30,6 +30,14 @@ class WalkConsts(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class SgnsParams(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("window", C.c_int32), ("negative", C.c_int32), ("epochs", C.c_int32),
+                ("epoch", C.c_int32), ("batch_words", C.c_int32), ("atomic_updates", C.c_int32),
+                ("reserved", C.c_int32), ("alpha", C.c_float), ("min_alpha", C.c_float), ("seed", C.c_uint64),
+                ("walk_offset", C.c_int64), ("total_walks", C.c_int64)]
+
+
+SGNS_STAT_NAMES = ("pairs", "tokens_kept", "negatives_skipped", "targets_clipped")
 WALK_STAT_NAMES = ("steps", "trials", "probes", "searches", "fold_hits", "fallbacks", "dead", "reserved")
 
 _P = C.c_void_p
@@ -51,6 +59,14 @@ _SIGNATURES = {
     "n2v_walk": (C.c_int, [C.POINTER(Graph), _P, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double,
                            C.c_uint64, _P, C.c_int64, _P, _P, _P]),
     "n2v_walk_consts": (C.c_int, [C.c_double, C.c_double, C.c_uint32, C.POINTER(WalkConsts)]),
+    "n2v_vocab_count": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
+    "n2v_sgns_prepare": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_double, C.c_double, _P, _P, _P,
+                                   C.POINTER(C.c_int64), _P]),
+    "n2v_sgns_init": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_uint64, _P]),
+    "n2v_sgns_exp_table": (C.c_int, [C.POINTER(C.c_float)]),
+    "n2v_sgns_train": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, _P, _P, C.c_int64, _P, _P, _P,
+                                 C.POINTER(SgnsParams), _P, _P, _P, C.c_int64, _P]),
+    "n2v_scale": (C.c_int, [_P, C.c_int64, C.c_float, _P]),
 }
 
 _lib = None
@@ -79,21 +95,8 @@ def load(build_if_missing: bool = True):
         fn = getattr(lib, name)  # AttributeError here = ABI mismatch, loudly
         fn.restype = res
         fn.argtypes = args
-    for name, (res, args) in _optional_signatures().items():
-        if hasattr(lib, name):
-            fn = getattr(lib, name)
-            fn.restype = res
-            fn.argtypes = args
     _lib = lib
     return lib
-
-
-def _optional_signatures():
-    try:
-        from ._lib_sgns import SIGNATURES
-        return SIGNATURES
-    except ImportError:
-        return {}
 
 
 def check(rc: int, what: str = ""):

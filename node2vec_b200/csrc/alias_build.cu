@@ -7,63 +7,12 @@
 // back, left-to-right fp64 sum), so one thread owns one vertex; vertices are independent.
 // fp64 is kept un-contracted (explicit __d*_rn intrinsics) so every intermediate rounds
 // exactly as CPython's float arithmetic does.
+#include "alias_core.cuh"
 #include "n2v_internal.cuh"
 
 namespace {
 
 constexpr int kBlock = 128;
-
-// sum(list) starting from int 0, as the interpreter evaluates it (see n2v_b200.h sum modes)
-template <typename F>
-__device__ double python_sum(F value, uint32_t n, int sum_mode) {
-  double total = value(0);  // 0 + v0 is exact
-  if (sum_mode == N2V_SUM_NAIVE) {
-    for (uint32_t i = 1; i < n; ++i) total = __dadd_rn(total, value(i));
-    return total;
-  }
-  double comp = 0.0;
-  for (uint32_t i = 1; i < n; ++i) {
-    const double v = value(i);
-    const double t = __dadd_rn(total, v);
-    if (fabs(total) >= fabs(v))
-      comp = __dadd_rn(comp, __dadd_rn(__dsub_rn(total, t), v));
-    else
-      comp = __dadd_rn(comp, __dadd_rn(__dsub_rn(v, t), total));
-    total = t;
-  }
-  if (comp != 0.0 && isfinite(comp)) total = __dadd_rn(total, comp);
-  return total;
-}
-
-// probs[] holds the raw weights on entry and the alias "probs" on exit.
-// stack[] is an n-slot int32 slice: the underfull list grows up from slot 0, the overfull
-// list grows down from slot n-1 (every index is on exactly one list, so they never meet).
-// Returns false when the weights sum to zero (reference: ZeroDivisionError).
-template <typename AliasStore>
-__device__ bool build_alias_one(double* __restrict__ probs, uint32_t n, int sum_mode,
-                                int32_t* __restrict__ stack, AliasStore store_alias) {
-  const double total = python_sum([&](uint32_t i) { return probs[i]; }, n, sum_mode);
-  const double mean = __ddiv_rn(total, static_cast<double>(n));
-  if (!(mean != 0.0)) return false;
-  int64_t n_small = 0, n_large = 0;  // list sizes
-  for (uint32_t i = 0; i < n; ++i) {
-    const double pr = __ddiv_rn(probs[i], mean);
-    probs[i] = pr;
-    store_alias(i, 0);
-    if (pr < 1.0) stack[n_small++] = static_cast<int32_t>(i);
-    else stack[n - 1 - (n_large++)] = static_cast<int32_t>(i);
-  }
-  while (n_small > 0 && n_large > 0) {
-    const int32_t lo = stack[--n_small];
-    const int32_t hi = stack[n - 1 - (--n_large)];
-    store_alias(static_cast<uint32_t>(lo), hi);
-    const double ph = __dsub_rn(__dadd_rn(probs[hi], probs[lo]), 1.0);
-    probs[hi] = ph;
-    if (ph < 1.0) stack[n_small++] = hi;
-    else stack[n - 1 - (n_large++)] = hi;
-  }
-  return true;
-}
 
 __device__ __forceinline__ uint32_t prob_to_thr(double pr) {
   // u32 < thr  <=>  u32 / 2^32 < pr   (exact for pr < 1); pr >= 1 saturates (alias_dst == dst there)
@@ -92,7 +41,7 @@ __global__ void alias_build_kernel(n2v_vertex_t* __restrict__ vtx, const int32_t
       wsum = __dadd_rn(wsum, w);
     }
     vtx[v].wsum = static_cast<float>(wsum);
-    const bool ok = build_alias_one(pr, n, sum_mode, scratch + base,
+    const bool ok = n2v::build_alias_one(pr, n, sum_mode, scratch + base,
                                     [&](uint32_t i, int32_t a) { out[i].alias_idx = a; });
     if (!ok) {
       atomicAdd(n_zero, 1ull);
@@ -155,7 +104,7 @@ __global__ void edge_alias_kernel(const n2v_vertex_t* __restrict__ vtx, const in
       else bw = __ddiv_rn(w, q);                               // anywhere else       (:229-230)
       pr[k] = bw;
     }
-    build_alias_one(pr, n, sum_mode, scratch + off, [&](uint32_t k, int32_t a) { al[k] = a; });
+    n2v::build_alias_one(pr, n, sum_mode, scratch + off, [&](uint32_t k, int32_t a) { al[k] = a; });
   }
 }
 

@@ -1,0 +1,357 @@
+// K3: skip-gram negative-sampling SGD over the walk matrix.
+//
+// Replaces gensim 3.8's train_batch_sg / w2v_fast_sentence_sg_neg as reached from
+// Node2VecGensim.fit (reference embedding.py:120-127) with sg=1, negative=K:
+//   per sentence : drop out-of-vocabulary and sub-sampled tokens; per centre i a reduced
+//                  window b in [0, window); contexts j in [i-window+b, i+window-b], j != i
+//   per pair     : input row syn0[walk[j]]; targets walk[i] (label 1) then K negatives drawn
+//                  ~ count^0.75 (label 0, skipped when equal to walk[i]); f = <in, target>;
+//                  skipped when |f| >= 6; s = EXP_TABLE[f]; g = (label - s) * alpha;
+//                  work += g * target; target += g * in; finally in += work.
+// All arithmetic fp32.
+//
+// Execution model.  One WARP per walk (sentence); the sentence lives in shared memory after
+// sub-sampling; rows are D fp32 held NV float4-per-lane in registers, so one row is one
+// coalesced 512-byte gather per 128 dims, the dot is NV fused multiply-adds per lane plus a
+// five-step butterfly, and the centre's positive row stays in registers across its whole
+// context window.  Row updates are Hogwild: `red.global.add.v4.f32` (no lost updates under
+// tens of thousands of concurrent warps) or plain stores (gensim's own lock-free behaviour).
+// This is a gather/scatter path -- (K+2) rows in, (K+2) rows out per pair -- so no tensor
+// cores; the walk buffer is read once per epoch.
+#include "n2v_internal.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kWarps = kBlock / 32;
+constexpr float kMaxExp = 6.0f;
+constexpr uint64_t kLcgMask = 281474976710655ULL;  // 2^48 - 1
+
+struct SgnsArgs {
+  const int32_t* walks;
+  const uint32_t* keep_thr;
+  const int2* neg_table;
+  const float* exp_table;
+  float* syn0;
+  float* syn1neg;
+  unsigned long long* stats;
+  int32_t* trace;
+  float* trace_alpha;
+  int64_t trace_cap;
+  int64_t n_walks, pitch, walk_offset, total_walks;
+  uint32_t n_vertices;
+  int32_t len, len_cap, dim, window, negative, epochs, epoch, batch_words;
+  float alpha, min_alpha;
+  uint32_t key0, key1;
+};
+
+__device__ __forceinline__ uint64_t lcg_next(uint64_t r) { return (r * 25214903917ULL + 11ULL) & kLcgMask; }
+
+template <int NV>
+struct Row {
+  float4 v[NV];
+};
+
+template <int NV>
+__device__ __forceinline__ Row<NV> load_row(const float* __restrict__ base, int32_t dim, int lane) {
+  Row<NV> r;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int d = (i * 32 + lane) * 4;
+    r.v[i] = d < dim ? *reinterpret_cast<const float4*>(base + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  return r;
+}
+
+template <int NV>
+__device__ __forceinline__ float dot_rows(const Row<NV>& a, const Row<NV>& b) {
+  float p = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    p = fmaf(a.v[i].x, b.v[i].x, p);
+    p = fmaf(a.v[i].y, b.v[i].y, p);
+    p = fmaf(a.v[i].z, b.v[i].z, p);
+    p = fmaf(a.v[i].w, b.v[i].w, p);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+  return p;
+}
+
+// acc += g * x
+template <int NV>
+__device__ __forceinline__ void axpy(Row<NV>& acc, float g, const Row<NV>& x) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    acc.v[i].x = fmaf(g, x.v[i].x, acc.v[i].x);
+    acc.v[i].y = fmaf(g, x.v[i].y, acc.v[i].y);
+    acc.v[i].z = fmaf(g, x.v[i].z, acc.v[i].z);
+    acc.v[i].w = fmaf(g, x.v[i].w, acc.v[i].w);
+  }
+}
+
+// global row += g * x  (ATOMIC: vector reduction; else read-modify-write of the value we loaded)
+template <int NV, bool ATOMIC>
+__device__ __forceinline__ void update_row(float* __restrict__ base, int32_t dim, int lane, float g,
+                                           const Row<NV>& x, const Row<NV>& loaded) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int d = (i * 32 + lane) * 4;
+    if (d < dim) {
+      float4* p = reinterpret_cast<float4*>(base + d);
+      if (ATOMIC) {
+        atomicAdd(p, make_float4(g * x.v[i].x, g * x.v[i].y, g * x.v[i].z, g * x.v[i].w));
+      } else {
+        *p = make_float4(fmaf(g, x.v[i].x, loaded.v[i].x), fmaf(g, x.v[i].y, loaded.v[i].y),
+                         fmaf(g, x.v[i].z, loaded.v[i].z), fmaf(g, x.v[i].w, loaded.v[i].w));
+      }
+    }
+  }
+}
+
+// global row += delta
+template <int NV, bool ATOMIC>
+__device__ __forceinline__ void add_row(float* __restrict__ base, int32_t dim, int lane, const Row<NV>& delta,
+                                        const Row<NV>& loaded) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int d = (i * 32 + lane) * 4;
+    if (d < dim) {
+      float4* p = reinterpret_cast<float4*>(base + d);
+      if (ATOMIC) {
+        atomicAdd(p, delta.v[i]);
+      } else {
+        *p = make_float4(loaded.v[i].x + delta.v[i].x, loaded.v[i].y + delta.v[i].y,
+                         loaded.v[i].z + delta.v[i].z, loaded.v[i].w + delta.v[i].w);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float sigmoid_table(const float* __restrict__ table, float f) {
+  return __ldg(table + static_cast<int>((f + kMaxExp) * (1000.0f / kMaxExp / 2.0f)));
+}
+
+template <int NV, bool ATOMIC>
+__global__ void __launch_bounds__(kBlock) sgns_kernel(const __grid_constant__ SgnsArgs A) {
+  extern __shared__ int32_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  int32_t* sent = smem + wib * A.len_cap;
+  const bool tracing = A.trace != nullptr;
+  if (tracing && (blockIdx.x != 0 || wib != 0)) return;   // trace mode: ONE warp, walks in order
+  const int64_t n_warps = tracing ? 1 : static_cast<int64_t>(gridDim.x) * kWarps;
+  unsigned long long c_pairs = 0, c_kept = 0, c_negskip = 0, c_clip = 0;
+  int64_t trace_pos = 0;
+  const int K = A.negative;
+  const double total_words = static_cast<double>(A.total_walks) * static_cast<double>(A.len);
+
+  for (int64_t s = tracing ? 0 : static_cast<int64_t>(blockIdx.x) * kWarps + wib; s < A.n_walks; s += n_warps) {
+    const int64_t gs = A.walk_offset + s;
+    // learning rate of this walk's job (gensim: linear decay, refreshed per batch_words words)
+    float alpha;
+    {
+      const int64_t job_start_words = (gs * A.len / A.batch_words) * static_cast<int64_t>(A.batch_words);
+      const double progress = (static_cast<double>(A.epoch) + static_cast<double>(job_start_words) / total_words) /
+                              static_cast<double>(A.epochs);
+      const double a = static_cast<double>(A.alpha) - (static_cast<double>(A.alpha) - static_cast<double>(A.min_alpha)) * progress;
+      alpha = static_cast<float>(a < static_cast<double>(A.min_alpha) ? static_cast<double>(A.min_alpha) : a);
+    }
+    // sub-sampling: position k is kept iff its token is in the vocabulary and u32 < keep_thr
+    int n = 0;
+    for (int k0 = 0; k0 < A.len; k0 += 32) {
+      const int k = k0 + lane;
+      int32_t tok = -1;
+      bool keep = false;
+      if (k < A.len) {
+        tok = __ldg(A.walks + s * A.pitch + k);
+        if (tok >= 0) {
+          const uint32_t thr = __ldg(A.keep_thr + tok);
+          if (thr == 0xFFFFFFFFu) keep = true;
+          else if (thr != 0u) {
+            const uint4 r = n2v::philox4x32_10(A.key0, A.key1, static_cast<uint32_t>(gs), static_cast<uint32_t>(gs >> 32),
+                                               static_cast<uint32_t>(A.epoch), 0x53554200u + static_cast<uint32_t>(k));
+            keep = r.x < thr;
+          }
+        }
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, keep);
+      if (keep) sent[n + __popc(m & ((1u << lane) - 1u))] = tok;
+      n += __popc(m);
+    }
+    __syncwarp();
+    c_kept += static_cast<unsigned long long>(n);
+    // per-walk 48-bit LCG (gensim's generator), seeded from Philox; identical in every lane
+    uint64_t rnd;
+    {
+      const uint4 r = n2v::philox4x32_10(A.key0, A.key1, static_cast<uint32_t>(gs), static_cast<uint32_t>(gs >> 32),
+                                         static_cast<uint32_t>(A.epoch), 0x4C434700u);
+      rnd = ((static_cast<uint64_t>(r.y) << 32) | r.x) & kLcgMask;
+    }
+    for (int i = 0; i < n; ++i) {
+      const uint32_t b = static_cast<uint32_t>(rnd >> 16) % static_cast<uint32_t>(A.window);
+      rnd = lcg_next(rnd);
+      int j0 = i - A.window + static_cast<int>(b), j1 = i + A.window + 1 - static_cast<int>(b);
+      if (j0 < 0) j0 = 0;
+      if (j1 > n) j1 = n;
+      if (j1 - j0 <= 1) continue;
+      const int32_t wi = sent[i];
+      float* pos_ptr = A.syn1neg + static_cast<int64_t>(wi) * A.dim;
+      Row<NV> pos = load_row<NV>(pos_ptr, A.dim, lane);   // stays in registers across the window
+      for (int j = j0; j < j1; ++j) {
+        if (j == i) continue;
+        const int32_t wj = sent[j];
+        float* in_ptr = A.syn0 + static_cast<int64_t>(wj) * A.dim;
+        const Row<NV> in = load_row<NV>(in_ptr, A.dim, lane);
+        Row<NV> work;
+#pragma unroll
+        for (int q = 0; q < NV; ++q) work.v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int32_t* trow = nullptr;
+        if (tracing && trace_pos < A.trace_cap) {
+          trow = A.trace + trace_pos * (2 + K);
+          if (lane == 0) { trow[0] = wi; trow[1] = wj; A.trace_alpha[trace_pos] = alpha; }
+        }
+        // positive target: the centre word
+        {
+          const float f = dot_rows<NV>(in, pos);
+          if (f > -kMaxExp && f < kMaxExp) {
+            const float g = (1.0f - sigmoid_table(A.exp_table, f)) * alpha;
+            axpy<NV>(work, g, pos);
+            update_row<NV, ATOMIC>(pos_ptr, A.dim, lane, g, in, pos);
+            axpy<NV>(pos, g, in);
+          } else {
+            ++c_clip;
+          }
+        }
+        // K negatives ~ count^0.75, one 8-byte alias gather each
+        for (int d = 0; d < K; ++d) {
+          const uint32_t u1 = static_cast<uint32_t>(rnd >> 16);
+          rnd = lcg_next(rnd);
+          const uint32_t u2 = static_cast<uint32_t>(rnd >> 16);
+          rnd = lcg_next(rnd);
+          const uint32_t slot = __umulhi(u1, A.n_vertices);
+          const int2 e = __ldg(A.neg_table + slot);
+          const int32_t tgt = (u2 < static_cast<uint32_t>(e.x)) ? static_cast<int32_t>(slot) : e.y;
+          if (tgt == wi) {
+            ++c_negskip;
+            if (trow && lane == 0) trow[2 + d] = -1;
+            continue;
+          }
+          if (trow && lane == 0) trow[2 + d] = tgt;
+          float* t_ptr = A.syn1neg + static_cast<int64_t>(tgt) * A.dim;
+          const Row<NV> tr = load_row<NV>(t_ptr, A.dim, lane);
+          const float f = dot_rows<NV>(in, tr);
+          if (f > -kMaxExp && f < kMaxExp) {
+            const float g = (0.0f - sigmoid_table(A.exp_table, f)) * alpha;
+            axpy<NV>(work, g, tr);
+            update_row<NV, ATOMIC>(t_ptr, A.dim, lane, g, in, tr);
+          } else {
+            ++c_clip;
+          }
+        }
+        add_row<NV, ATOMIC>(in_ptr, A.dim, lane, work, in);
+        ++c_pairs;
+        if (tracing) ++trace_pos;
+      }
+    }
+    __syncwarp();
+  }
+  if (A.stats && lane == 0) {
+    if (c_pairs) atomicAdd(A.stats + 0, c_pairs);
+    if (c_kept) atomicAdd(A.stats + 1, c_kept);
+    if (c_negskip) atomicAdd(A.stats + 2, c_negskip);
+    if (c_clip) atomicAdd(A.stats + 3, c_clip);
+  }
+}
+
+template <int NV>
+cudaError_t launch(const SgnsArgs& A, bool atomic, int grid, size_t smem, cudaStream_t stream) {
+  if (atomic) sgns_kernel<NV, true><<<grid, kBlock, smem, stream>>>(A);
+  else sgns_kernel<NV, false><<<grid, kBlock, smem, stream>>>(A);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" int n2v_sgns_train(const int32_t* walks, int64_t n_walks, int32_t len, int64_t pitch,
+                              const uint32_t* keep_thr, const int32_t* neg_table, int64_t n_vertices,
+                              float* syn0, float* syn1neg, const float* exp_table,
+                              const n2v_sgns_params_t* P, uint64_t* stats, int32_t* trace, float* trace_alpha,
+                              int64_t trace_cap, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  N2V_CHECK_ARG(P != nullptr, "n2v_sgns_train: params is NULL");
+  N2V_CHECK_ARG(P->dim >= 4 && P->dim <= 1024 && P->dim % 4 == 0,
+                "n2v_sgns_train: dim %d must be a multiple of 4 in [4, 1024]", P->dim);
+  N2V_CHECK_ARG(P->window >= 1 && P->negative >= 1 && P->negative <= 64,
+                "n2v_sgns_train: window (%d) must be >= 1 and negative (%d) in [1, 64]", P->window, P->negative);
+  N2V_CHECK_ARG(P->epochs >= 1 && P->epoch >= 0 && P->epoch < P->epochs && P->batch_words >= 1,
+                "n2v_sgns_train: bad epoch schedule");
+  N2V_CHECK_ARG(n_walks >= 0 && len >= 1 && pitch >= len && len <= 10000,
+                "n2v_sgns_train: bad walk matrix shape (sentences are capped at 10000 tokens)");
+  N2V_CHECK_ARG(n_vertices > 0 && n_vertices < (int64_t(1) << 31), "n2v_sgns_train: n_vertices out of range");
+  if (n_walks == 0) return N2V_OK;
+  N2V_CHECK_ARG(walks && keep_thr && neg_table && syn0 && syn1neg && exp_table, "n2v_sgns_train: NULL buffer");
+  N2V_CHECK_ARG(trace == nullptr || trace_alpha != nullptr, "n2v_sgns_train: trace needs trace_alpha");
+  N2V_CHECK_ARG((reinterpret_cast<uintptr_t>(syn0) & 15) == 0 && (reinterpret_cast<uintptr_t>(syn1neg) & 15) == 0,
+                "n2v_sgns_train: tables must be 16-byte aligned");
+
+  SgnsArgs A{};
+  A.walks = walks;
+  A.keep_thr = keep_thr;
+  A.neg_table = reinterpret_cast<const int2*>(neg_table);
+  A.exp_table = exp_table;
+  A.syn0 = syn0;
+  A.syn1neg = syn1neg;
+  A.stats = reinterpret_cast<unsigned long long*>(stats);
+  A.trace = trace;
+  A.trace_alpha = trace_alpha;
+  A.trace_cap = trace_cap;
+  A.n_walks = n_walks;
+  A.pitch = pitch;
+  A.walk_offset = P->walk_offset;
+  A.total_walks = P->total_walks > 0 ? P->total_walks : n_walks;
+  A.n_vertices = static_cast<uint32_t>(n_vertices);
+  A.len = len;
+  A.len_cap = (len + 31) & ~31;
+  A.dim = P->dim;
+  A.window = P->window;
+  A.negative = P->negative;
+  A.epochs = P->epochs;
+  A.epoch = P->epoch;
+  A.batch_words = P->batch_words;
+  A.alpha = P->alpha;
+  A.min_alpha = P->min_alpha;
+  A.key0 = static_cast<uint32_t>(P->seed);
+  A.key1 = static_cast<uint32_t>(P->seed >> 32);
+
+  const size_t smem = static_cast<size_t>(A.len_cap) * kWarps * sizeof(int32_t);
+  N2V_CHECK_ARG(smem <= 200 * 1024, "n2v_sgns_train: walk too long for shared-memory staging");
+  int grid;
+  if (trace) grid = 1;  // the kernel lets only warp 0 work in trace mode
+  else {
+    const int64_t need = (n_walks + kWarps - 1) / kWarps;
+    const int64_t cap = int64_t(n2v::kSmCount) * 8;
+    grid = static_cast<int>(need < cap ? need : cap);
+  }
+  const int nv = (P->dim + 127) / 128;
+  cudaError_t err;
+  const bool atomic = P->atomic_updates != 0;
+#define N2V_SGNS_LAUNCH(NVV)                                                                           \
+  do {                                                                                                 \
+    if (smem > 48 * 1024) {                                                                            \
+      cudaFuncSetAttribute(sgns_kernel<NVV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      cudaFuncSetAttribute(sgns_kernel<NVV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    }                                                                                                  \
+    err = launch<NVV>(A, atomic, grid, smem, stream);                                                  \
+  } while (0)
+  if (nv <= 1) N2V_SGNS_LAUNCH(1);
+  else if (nv <= 2) N2V_SGNS_LAUNCH(2);
+  else if (nv <= 4) N2V_SGNS_LAUNCH(4);
+  else N2V_SGNS_LAUNCH(8);
+#undef N2V_SGNS_LAUNCH
+  if (err != cudaSuccess) {
+    n2v::set_error("n2v_sgns_train: launch failed: %s", cudaGetErrorString(err));
+    return N2V_ERR_CUDA;
+  }
+  return N2V_OK;
+}

@@ -33,7 +33,7 @@ namespace {
 
 constexpr int kBlock = 256;
 #ifndef N2V_WALK_BLOCKS_PER_SM
-#define N2V_WALK_BLOCKS_PER_SM 8
+#define N2V_WALK_BLOCKS_PER_SM 5  // measured on B200: 5 (48 regs, no hot-path spills) beats 8/6/4/3
 #endif
 constexpr int kBlocksPerSm = N2V_WALK_BLOCKS_PER_SM;
 constexpr int kStage = 8;  // ids per lane per flush = one 32 B sector

@@ -200,3 +200,72 @@ def replay_walk(base, deg, arc_thr, arc_dst, arc_alias_dst, col, weight, graph_f
             list(ex.map(run, range(threads)))
     names = ["steps", "trials", "probes", "searches", "fold_hits", "fallbacks", "dead", "reserved"]
     return walks, alive.astype(bool), dict(zip(names, stats.sum(axis=0).tolist()))
+
+
+# ---------------------------------------------------------------------------------------
+# SGNS (gensim 3.8 restatement, oracle/csrc/sgns_ref.c) -- PARITY UNPINNED, see the C header
+# ---------------------------------------------------------------------------------------
+def sgns_exp_table():
+    lib = load()
+    out = np.zeros(1000, dtype=np.float32)
+    lib.orc_sgns_exp_table(_ptr(out, C.c_float))
+    return out
+
+
+def sgns_vocab(counts, min_count=5, sample=1e-3, ns_exponent=0.75):
+    """prepare_vocab + make_cum_table.  Returns (keep_int[V] uint64, order[n] ids by
+    descending count, cum_table[n] uint32)."""
+    lib = load()
+    lib.orc_sgns_vocab.restype = C.c_int64
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    V = len(counts)
+    keep = np.zeros(V, dtype=np.uint64)
+    order = np.zeros(V, dtype=np.int32)
+    cum = np.zeros(V, dtype=np.uint32)
+    n = lib.orc_sgns_vocab(_ptr(counts, C.c_int64), C.c_int64(V), C.c_int64(min_count), C.c_double(sample),
+                           C.c_double(ns_exponent), _ptr(keep, C.c_uint64), _ptr(order, C.c_int32),
+                           _ptr(cum, C.c_uint32))
+    return keep, order[:n].copy(), cum[:n].copy()
+
+
+def sgns_init(n_rows, dim, seed):
+    """gensim reset_weights law: (U[0,1) - 0.5) / dim per component, zeros for syn1neg."""
+    rng = np.random.RandomState(seed & 0xFFFFFFFF)
+    syn0 = ((rng.rand(n_rows, dim) - 0.5) / dim).astype(np.float32)
+    return syn0, np.zeros((n_rows, dim), dtype=np.float32)
+
+
+def sgns_train(walks, counts, syn0, syn1neg, window=5, negative=5, alpha=0.025, min_alpha=1e-4, epochs=5,
+               min_count=5, sample=1e-3, ns_exponent=0.75, batch_words=10000, seed=1, threads=1):
+    """gensim-3.8 skip-gram negative sampling over a rectangular walk matrix (in-place on
+    syn0 / syn1neg).  threads > 1 = lock-free workers on the same tables, like gensim."""
+    lib = load()
+    lib.orc_sgns_train.restype = C.c_int64
+    walks = np.ascontiguousarray(walks, dtype=np.int32)
+    W, length = walks.shape
+    keep, order, cum = sgns_vocab(counts, min_count, sample, ns_exponent)
+    D = syn0.shape[1]
+    pairs = 0
+    for ep in range(epochs):
+        def run(i):
+            lo, hi = W * i // threads, W * (i + 1) // threads
+            return lib.orc_sgns_train(
+                _ptr(walks, C.c_int32), C.c_int64(W), C.c_int64(length), C.c_int64(length), _ptr(keep, C.c_uint64),
+                _ptr(order, C.c_int32), _ptr(cum, C.c_uint32), C.c_int64(len(order)), _ptr(syn0, C.c_float),
+                _ptr(syn1neg, C.c_float), C.c_int64(D), C.c_int(window), C.c_int(negative), C.c_double(alpha),
+                C.c_double(min_alpha), C.c_int(ep), C.c_int(epochs), C.c_int64(batch_words), C.c_uint64(seed),
+                C.c_int64(lo), C.c_int64(hi))
+        if threads == 1:
+            pairs += run(0)
+        else:
+            with ThreadPoolExecutor(threads) as ex:
+                pairs += sum(ex.map(run, range(threads)))
+    return int(pairs)
+
+
+def sgns_apply_trace(trace, alphas, n_pairs, K, syn0, syn1neg):
+    lib = load()
+    trace = np.ascontiguousarray(trace, dtype=np.int32)
+    alphas = np.ascontiguousarray(alphas, dtype=np.float32)
+    lib.orc_sgns_apply_trace(_ptr(trace, C.c_int32), C.c_int64(n_pairs), C.c_int(K), _ptr(alphas, C.c_float),
+                             _ptr(syn0, C.c_float), _ptr(syn1neg, C.c_float), C.c_int64(syn0.shape[1]))
