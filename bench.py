@@ -156,6 +156,35 @@ def _cpu_walk_chunk(a):
     return steps, time.perf_counter() - t0, done
 
 
+SGNS_HP = dict(window=5, negative=5, alpha=0.025, min_alpha=1e-4, min_count=1, sample=1e-3)
+
+
+def sgns_bytes_per_pair(dim, negative):
+    """(K+2) rows read + (K+2) rows written, D fp32 each, no reuse assumed."""
+    return 8.0 * dim * (negative + 2)
+
+
+def cpu_baseline_sgns(walks, n_rows, dim, budget_s=12.0, threads=None):
+    """gensim-3.8 SGNS restatement (oracle/csrc/sgns_ref.c) with lock-free host threads on a
+    bounded sample of the same walk matrix: as many leading walks as fit the time budget."""
+    from oracle import clib
+    threads = threads or os.cpu_count() or 1
+    counts = np.bincount(walks.reshape(-1), minlength=n_rows)
+    syn0, syn1 = clib.sgns_init(n_rows, dim, 1)
+    n = min(len(walks), 2000 * threads)
+    pairs, dt = 0, 0.0
+    lo = 0
+    while dt < budget_s and lo < len(walks):
+        t0 = time.perf_counter()
+        pairs += clib.sgns_train(walks[lo:lo + n], counts, syn0, syn1, epochs=1, seed=1, batch_words=10000,
+                                 threads=threads, **SGNS_HP)
+        dt += time.perf_counter() - t0
+        lo += n
+    return {"value": pairs / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": f"first {min(lo, len(walks))} walks x {walks.shape[1]} tokens, 1 epoch = {pairs} pairs in {dt:.1f}s, "
+                      f"{threads} lock-free threads (oracle gensim-3.8 restatement; gensim itself is not installable)"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port) for the same metric/config."""
     rank = int(os.environ.get("RANK", "0"))
@@ -170,6 +199,14 @@ def run_reference(args):
         vals.append(base["value"])
     v = float(np.mean(vals))
     steps_per_pass = len(np.unique(make_graph(name)[0])) * w["num_walks"] * w["walk_length"]
+    # SGNS leg: walks for the sample come from the oracle's C port of the reference walk
+    from oracle import clib
+    src, dst = make_graph(name)
+    row_ptr, col, ws, _ = clib.csr_from_arcs(src, dst, None, w["n"])
+    starts = np.flatnonzero(np.diff(row_ptr) > 0).astype(np.int32)
+    walks_cpu, alive = clib.reference_walk(row_ptr, col, ws, starts, 4, w["walk_length"], w["p"], w["q"], "naive",
+                                           None, threads=os.cpu_count() or 1)
+    sgns_base = cpu_baseline_sgns(walks_cpu[alive], w["n"], w["dim"])
     line = {
         "impl": "reference", "metric": "walk_steps_per_s", "value": v, "unit": "walk-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -179,11 +216,112 @@ def run_reference(args):
                    "note": "ms_per_step extrapolates the sampled rate to one full pass"},
         "cpu_baseline": {**base, "value": v},
         "e2e": {"value": v, "unit": "walk-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "sgns": {"metric": "sgns_pairs_per_s", "value": sgns_base["value"], "unit": "pairs/s",
+                 "cpu_baseline": sgns_base,
+                 "e2e": {"value": sgns_base["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0,
+                         "d2h_bytes_per_step": 0}},
     }
     print(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------
+def bench_sgns(args, torch, dist, dev, world, rank, walks, w, flush, host_walks):
+    """Timed region: `steps` SGNS epochs (one kernel launch each; + the NCCL model-averaging
+    allreduce when world > 1) over the walk matrix already in HBM.  e2e: host walk matrix in,
+    Node2VecGensim.fit() (H2D + vocab + tables + init + 1 epoch), host embeddings out."""
+    from node2vec_b200.embedding import Node2VecGensim
+    from node2vec_b200.sgns import Word2Vec
+    dim, K = w["dim"], SGNS_HP["negative"]
+    group = dist.group.WORLD if world > 1 else None
+    m = Word2Vec(size=dim, sg=1, iter=args.steps + args.warmup, seed=1, batch_words=10000, process_group=group,
+                 **SGNS_HP)
+    m.build_vocab(walks)
+    for _ in range(args.warmup):
+        flush.fill_(1)
+        m.train(walks, epochs=1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    pairs = 0
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        m.train(walks, epochs=1)       # one n2v_sgns_train launch (+ allreduce/scale when world > 1)
+        b.record()
+        pairs += m.train_stats["pairs"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    tot = torch.tensor([float(sum(ms)), float(pairs)], device=dev, dtype=torch.float64)
+    if world > 1:
+        t_max = tot[:1].clone()
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        p_sum = tot[1:].clone()
+        dist.all_reduce(p_sum, op=dist.ReduceOp.SUM)
+        total_ms, total_pairs = float(t_max.item()), float(p_sum.item())
+    else:
+        total_ms, total_pairs = float(tot[0].item()), float(tot[1].item())
+    value = total_pairs / (total_ms * 1e-3)
+
+    # end to end through the reference-shaped API, host buffers both ways (rank-local)
+    def e2e_pass():
+        n2v = Node2VecGensim(_HostWalks(host_walks), {"sg": 1, "iter": 1, "size": dim, **SGNS_HP}, random_seed=1)
+        model = n2v.fit()
+        vec = model.wv.vectors          # host numpy (D2H inside fit)
+        return model.train_stats["pairs"], vec.nbytes
+    e2e_pass()
+    t0 = time.perf_counter()
+    n_e2e = 2
+    p_e2e = 0
+    for _ in range(n_e2e):
+        pe, d2h = e2e_pass()
+        p_e2e += pe
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    e2e_p = torch.tensor([float(p_e2e)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_p, op=dist.ReduceOp.SUM)
+    peak, peak_src = measured_peaks()
+    b_pair = sgns_bytes_per_pair(dim, K)
+    kernel_ms = float(np.mean(ms))
+    achieved = (pairs / args.steps) * b_pair / (kernel_ms * 1e-3) / 1e9
+    return {
+        "metric": "sgns_pairs_per_s", "value": value, "unit": "pairs/s", "ms_per_step": total_ms / args.steps,
+        "dtype": "f32", "gpu_launches": args.steps,
+        "config": {"dim": dim, **SGNS_HP, "walks_per_gpu": int(walks.shape[0]), "tokens_per_walk": int(walks.shape[1]),
+                   "updates": "red.global.add.v4.f32", "sync": "allreduce(avg) of both tables every epoch" if world > 1 else "none",
+                   "l2": "flushed between timed iterations; tables (2 x %.1f MB) are L2-resident" % (w["n"] * dim * 4 / 1e6)},
+        "e2e": {"value": float(e2e_p.item()) / float(e2e_t.item()), "unit": "pairs/s",
+                "h2d_bytes_per_step": int(host_walks.numel() * 4), "d2h_bytes_per_step": int(d2h),
+                "what": "Node2VecGensim(host walks).fit(): H2D + vocab_count + sgns_prepare + init + 1 epoch + D2H vectors"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "sgns_kernel", "bytes_per_pair": b_pair, "kernel_ms": kernel_ms,
+                     "pairs_per_launch": pairs / args.steps, "peak_source": peak_src},
+    }
+
+
+class _HostWalks:
+    """A [src, walk] frame stand-in whose walk matrix is a pinned host tensor."""
+
+    def __init__(self, t):
+        self._t = t
+
+    def __getitem__(self, key):
+        assert key == "walk"
+        return _Col(self._t)
+
+
+class _Col:
+    def __init__(self, t):
+        self._t = t
+
+    def tolist(self):
+        return self._t.numpy()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,6 +330,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="blogcatalog_like", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sgns", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -276,6 +415,11 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * steps_per_pass / float(e2e_s.item())
 
+    # ---- SGNS half: one epoch of skip-gram negative sampling over this rank's walk matrix
+    sgns = None
+    if not args.no_sgns:
+        sgns = bench_sgns(args, torch, dist, dev, world, rank, out[:, : w["walk_length"] + 1], w, flush, host_out)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -291,7 +435,7 @@ def main():
         "config": {"workload": name, **{k: w[k] for k in ("graph", "p", "q", "num_walks", "walk_length")},
                    "walkers_per_gpu": W, "arcs": int(g.n_arcs), "l2": "flushed between timed iterations (256 MiB write)",
                    "sharding": "replicated CSR, walkers sharded by (start vertex, walk number); no collective"},
-        "gpu_launches": args.steps,
+        "gpu_launches": args.steps + (sgns["gpu_launches"] if sgns else 0),
         "e2e": {"value": e2e_value, "unit": "walk-steps/s",
                 "h2d_bytes_per_step": int(src_pin.numel() * 4 + dst_pin.numel() * 4),
                 "d2h_bytes_per_step": int(host_out.numel() * 4),
@@ -303,8 +447,14 @@ def main():
         "clocks": clocks.summary(),
         "walk_stats": stats,
     }
+    if sgns:
+        sgns.pop("gpu_launches")
+        line["sgns"] = sgns
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_walk(name)
+        if sgns:
+            sample = host_out.numpy()
+            line["sgns"]["cpu_baseline"] = cpu_baseline_sgns(sample, w["n"], w["dim"])
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define N2V_ABI_VERSION 2
+#define N2V_ABI_VERSION 3
 #define N2V_MAX_PARTS 16
 
 /* error codes */
@@ -59,16 +59,17 @@ enum {
 typedef struct n2v_vertex {
   uint32_t base;  /* index of the first out-arc in arcs[] / col[] / weight[] */
   uint32_t deg;   /* number of out-arcs */
-  uint32_t hbase; /* index of the first 32-byte bucket of this vertex's neighbour hash set in hash[] */
+  uint32_t hbase; /* first 32-byte bucket of this vertex's neighbour hash set: (base >> 2) + local vertex index */
   float wsum;     /* (float) of the fp64 left-to-right sum of out-weights (weighted return-edge fold) */
 } n2v_vertex_t;
 
 /* Neighbour hash set of a vertex: the membership test "x in N_out(t)" of
  * generate_edge_alias_tables (randomwalk.py:226, a Python set) as ONE 32-byte gather.
- * Vertex t owns n2v_hash_nbuckets(deg) consecutive buckets of 8 int32 slots (load <= 0.5),
- * filled by linear probing over buckets in col[] order; empty slots hold N2V_HASH_EMPTY and
- * a bucket's used slots are contiguous from slot 0.
- *   bucket(x) = mulhi32(x * 0x9E3779B1, nbuckets) */
+ * Vertex t owns n2v_hash_nbuckets(deg) consecutive buckets of 8 int32 slots (load <= 0.5)
+ * starting at bucket n2v_hash_base(base, local index) -- derivable from what a walker
+ * already holds, so no extra gather -- filled by linear probing over buckets in col[]
+ * order; empty slots hold N2V_HASH_EMPTY and a bucket's used slots are contiguous from
+ * slot 0.   bucket(x) = mulhi32(x * 0x9E3779B1, nbuckets) */
 #define N2V_HASH_SLOTS 8
 #define N2V_HASH_EMPTY (-1)
 #define N2V_HASH_MULT 0x9E3779B1u
@@ -78,19 +79,28 @@ typedef struct n2v_vertex {
 #define N2V_HD
 #endif
 static inline N2V_HD uint32_t n2v_hash_nbuckets(uint32_t deg) { return (deg + 3u) >> 2; }
+/* floor(base/4) + v leaves every vertex at least ceil(deg/4) buckets: total <= n_arcs/4 + n_vertices */
+static inline N2V_HD uint32_t n2v_hash_base(uint32_t base, uint32_t local_vertex) { return (base >> 2) + local_vertex; }
 
 /* One out-arc with its FIRST-ORDER alias-table entry folded in: replaces the
- * (alias[k], probs[k]) pair of generate_alias_tables (randomwalk.py:157-190) plus the
- * neighbour id, so that one alias draw is ONE 16-byte gather.
+ * (alias[k], probs[k]) pair of generate_alias_tables (randomwalk.py:157-190), the
+ * neighbour id AND the adjacency header of whichever vertex the draw lands on (the
+ * reference's next join, fugue.py:147), so that one walk trial is ONE 32-byte gather
+ * (one DRAM/L2 sector, one LDG.256 on sm_100a) with no dependent vertex lookup.
  *   thr       = min(ceil(probs[k] * 2^32), 2^32 - 1): `u32 < thr`  <=>  `r2 < probs[k]`
  *   dst       = neighbour id at index k          (taken when u32 <  thr)
  *   alias_dst = neighbour id at index alias[k]   (taken when u32 >= thr); == dst when probs[k] >= 1
- *   alias_idx = alias[k] exactly as the reference computes it */
+ *   alias_idx = alias[k] exactly as the reference computes it
+ *   dst_base / dst_deg, adst_base / adst_deg = vtx[dst] / vtx[alias_dst] (part-local base) */
 typedef struct n2v_arc {
   uint32_t thr;
   int32_t dst;
   int32_t alias_dst;
   int32_t alias_idx;
+  uint32_t dst_base;
+  uint32_t dst_deg;
+  uint32_t adst_base;
+  uint32_t adst_deg;
 } n2v_arc_t;
 
 /* One vertex-range shard of the CSR.  A replicated graph has exactly one part that
@@ -147,13 +157,11 @@ int n2v_csr_build(const int32_t* src, const int32_t* dst, const double* weight, 
 /* ---- K0b: neighbour hash sets -----------------------------------------------------
  * Replaces `set(Neighbors(src_nbs).dst_id)` (randomwalk.py:318), built once per vertex
  * instead of once per walker per step.  hash: [n_buckets_cap][8] int32 with
- * n_buckets_cap >= n2v_hash_buckets_bound(); fills vtx[].hbase; *n_buckets_host = buckets
- * used (synchronises the stream to return it). */
+ * n_buckets_cap >= n2v_hash_buckets_bound() = n_arcs/4 + n_vertices + 1; fills vtx[].hbase.
+ * Asynchronous. */
 int64_t n2v_hash_buckets_bound(int64_t n_arcs, int64_t n_vertices);
-size_t n2v_hash_scratch_bytes(int64_t n_vertices);
 int n2v_hash_build(n2v_vertex_t* vtx, const int32_t* col, int64_t n_vertices, int64_t n_arcs,
-                   int32_t* hash, int64_t n_buckets_cap, void* scratch, size_t scratch_bytes,
-                   int64_t* n_buckets_host, void* stream);
+                   int32_t* hash, int64_t n_buckets_cap, void* stream);
 
 /* ---- K1: per-vertex first-order alias tables, bit-exact fp64 ------------------------
  * Replaces generate_alias_tables (randomwalk.py:157-190) for every vertex at once (the

@@ -48,9 +48,7 @@ _SIGNATURES = {
     "n2v_csr_build": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t,
                                 C.POINTER(C.c_uint32), _P]),
     "n2v_hash_buckets_bound": (C.c_int64, [C.c_int64, C.c_int64]),
-    "n2v_hash_scratch_bytes": (C.c_size_t, [C.c_int64]),
-    "n2v_hash_build": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, C.c_int64, _P, C.c_size_t,
-                                 C.POINTER(C.c_int64), _P]),
+    "n2v_hash_build": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
     "n2v_alias_build": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P, _P, _P,
                                   C.POINTER(C.c_int64), _P]),
     "n2v_edge_alias_build": (C.c_int, [C.POINTER(Graph), _P, _P, C.c_int64, C.c_double, C.c_double, C.c_int,

@@ -47,7 +47,8 @@ __global__ void alias_build_kernel(n2v_vertex_t* __restrict__ vtx, const int32_t
       atomicAdd(n_zero, 1ull);
       for (uint32_t i = 0; i < n; ++i) {
         pr[i] = 0.0;
-        out[i] = n2v_arc_t{0xFFFFFFFFu, col[base + i], col[base + i], 0};
+        const int32_t x = col[base + i];
+        out[i] = n2v_arc_t{0xFFFFFFFFu, x, x, 0, vtx[x].base, vtx[x].deg, vtx[x].base, vtx[x].deg};
         if (alias) alias[base + i] = 0;
       }
       continue;
@@ -61,6 +62,11 @@ __global__ void alias_build_kernel(n2v_vertex_t* __restrict__ vtx, const int32_t
       rec.dst = self;
       rec.alias_dst = (p >= 1.0) ? self : col[base + a];
       rec.alias_idx = a;
+      // adjacency headers of both possible landing vertices (deg is final; base too: K0 ran before)
+      rec.dst_base = vtx[rec.dst].base;
+      rec.dst_deg = vtx[rec.dst].deg;
+      rec.adst_base = vtx[rec.alias_dst].base;
+      rec.adst_deg = vtx[rec.alias_dst].deg;
       out[i] = rec;
       if (alias) alias[base + i] = a;
     }

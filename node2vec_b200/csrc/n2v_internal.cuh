@@ -38,8 +38,18 @@ __device__ __forceinline__ uint4 load_vtx(const n2v_vertex_t* p) {
   return __ldg(reinterpret_cast<const uint4*>(p));
 }
 
-__device__ __forceinline__ int4 load_arc(const n2v_arc_t* p) {
-  return __ldg(reinterpret_cast<const int4*>(p));
+// 32 bytes in ONE request (LDG.E.256, new on sm_100): an arc record or a hash bucket is
+// exactly one L2/DRAM sector.  Read-only (.nc) path.
+struct Int8 {
+  int32_t a[8];
+};
+__device__ __forceinline__ Int8 load_sector(const void* p) {
+  Int8 r;
+  asm volatile("ld.global.nc.v8.s32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.a[0]), "=r"(r.a[1]), "=r"(r.a[2]), "=r"(r.a[3]), "=r"(r.a[4]), "=r"(r.a[5]), "=r"(r.a[6]),
+                 "=r"(r.a[7])
+               : "l"(p));
+  return r;
 }
 
 // ---- Philox4x32-10 (Salmon et al., SC'11), counter-based ------------------------------

@@ -12,9 +12,10 @@
 // the current vertex v, is  P(x) ~ w(v,x) * alpha(t,x)  with alpha = 1/p (x == t),
 // 1 (x in N_out(t)), 1/q (otherwise) (randomwalk.py:223-230).  We draw from exactly that
 // law without building the per-(t,v) table: propose x from v's FIRST-ORDER alias table
-// (one 16-byte gather), accept with alpha/cap; membership in N_out(t) is one 32-byte
-// gather from t's bucketed hash set and is skipped whenever the accept draw already
-// decides (u below both thresholds / above both).  The return arc's excess mass (1/p above
+// (one 32-byte gather that also carries x's adjacency header, so an accepted step needs no
+// further lookup), accept with alpha/cap; membership in N_out(t) is one 32-byte gather
+// from t's bucketed hash set and is skipped whenever the accept draw already decides
+// (u below both thresholds / above both).  Both gathers are single LDG.256 requests.  The return arc's excess mass (1/p above
 // cap) is a separate mixture component (the "fold"), so small p does not inflate the
 // envelope.
 //
@@ -33,7 +34,7 @@ namespace {
 
 constexpr int kBlock = 256;
 #ifndef N2V_WALK_BLOCKS_PER_SM
-#define N2V_WALK_BLOCKS_PER_SM 5  // measured on B200: 5 (48 regs, no hot-path spills) beats 8/6/4/3
+#define N2V_WALK_BLOCKS_PER_SM 6  // measured on B200 (v3 kernel): 6 blocks = 40 regs beats 8 (spills) and 5
 #endif
 constexpr int kBlocksPerSm = N2V_WALK_BLOCKS_PER_SM;
 constexpr int kStage = 8;  // ids per lane per flush = one 32 B sector
@@ -62,12 +63,12 @@ __device__ __forceinline__ bool member(const int32_t* __restrict__ hash, uint32_
   const uint32_t nb = n2v_hash_nbuckets(deg);
   uint32_t b = __umulhi(static_cast<uint32_t>(x) * N2V_HASH_MULT, nb);
   for (;;) {
-    const int4* p = reinterpret_cast<const int4*>(hash + (static_cast<size_t>(hbase) + b) * N2V_HASH_SLOTS);
-    const int4 lo = __ldg(p), hi = __ldg(p + 1);
+    const n2v::Int8 s = n2v::load_sector(hash + (static_cast<size_t>(hbase) + b) * N2V_HASH_SLOTS);
     ++probes;
-    if (lo.x == x || lo.y == x || lo.z == x || lo.w == x || hi.x == x || hi.y == x || hi.z == x || hi.w == x)
+    if (s.a[0] == x || s.a[1] == x || s.a[2] == x || s.a[3] == x || s.a[4] == x || s.a[5] == x || s.a[6] == x ||
+        s.a[7] == x)
       return true;
-    if (hi.w == N2V_HASH_EMPTY) return false;  // bucket not full: x would have been here
+    if (s.a[7] == N2V_HASH_EMPTY) return false;  // bucket not full: x would have been here
     b = (b + 1 == nb) ? 0u : b + 1;
   }
 }
@@ -130,7 +131,7 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
 
   // walker state (offsets are 32-bit: a part holds < 2^32 arcs / buckets)
   int32_t t = -1, v = 0, pos = 0;
-  uint32_t deg_t = 0, deg_v = 0, base_v = 0, base_t = 0, hbase_v = 0, hbase_t = 0;
+  uint32_t deg_t = 0, deg_v = 0, base_v = 0, base_t = 0;
   uint32_t trial = 0, thr_out = 0, wid_lo = 0, wid_hi = 0;
   uint32_t part_v = 0, part_t = 0;
   bool active = false;
@@ -164,17 +165,16 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
     active = false;
     w += stride;
   };
-  auto enter = [&](int32_t x, uint32_t& part, uint32_t& base, uint32_t& deg, uint32_t& hbase) {
-    uint32_t local = static_cast<uint32_t>(x);
-    part = 0;
-    if (MULTI) {
-      part = static_cast<uint32_t>(x / g.part_size);
-      local = static_cast<uint32_t>(x - part * g.part_size);
-    }
-    const uint4 rec = n2v::load_vtx(g.parts[part].vtx + local);
+  auto part_of = [&](int32_t x) -> uint32_t { return MULTI ? static_cast<uint32_t>(x / g.part_size) : 0u; };
+  auto local_of = [&](int32_t x, uint32_t part) -> uint32_t {
+    return MULTI ? static_cast<uint32_t>(x - part * g.part_size) : static_cast<uint32_t>(x);
+  };
+  // adjacency header by vertex id: only at walk start and after the (rare) exact fallback
+  auto enter = [&](int32_t x, uint32_t& part, uint32_t& base, uint32_t& deg) {
+    part = part_of(x);
+    const uint4 rec = n2v::load_vtx(g.parts[part].vtx + local_of(x, part));
     base = rec.x;
     deg = rec.y;
-    hbase = rec.z;
   };
 
   for (;;) {
@@ -187,7 +187,7 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
       const uint64_t walk_id = static_cast<uint64_t>(static_cast<uint32_t>(v)) * static_cast<uint32_t>(A.num_walks) + r;
       wid_lo = static_cast<uint32_t>(walk_id);
       wid_hi = static_cast<uint32_t>(walk_id >> 32);
-      enter(v, part_v, base_v, deg_v, hbase_v);
+      enter(v, part_v, base_v, deg_v);
       t = -1;
       pos = 0;
       trial = 0;
@@ -203,14 +203,20 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
     const bool first = (pos == 0);
     bool accept;
     int32_t x;
+    uint32_t base_x, deg_x;   // adjacency header of x, delivered with the proposal
     if (FOLD && !first && rnd.x < thr_out) {
       x = t;
+      base_x = base_t;
+      deg_x = deg_t;
       accept = true;
       if (STATS) ++c_fold;
     } else {
       const uint32_t k = __umulhi(rnd.y, deg_v);
-      const int4 arc = n2v::load_arc(g.parts[MULTI ? part_v : 0].arcs + base_v + k);
-      x = (rnd.z < static_cast<uint32_t>(arc.x)) ? arc.y : arc.z;
+      const n2v::Int8 arc = n2v::load_sector(g.parts[MULTI ? part_v : 0].arcs + base_v + k);
+      const bool self = rnd.z < static_cast<uint32_t>(arc.a[0]);
+      x = self ? arc.a[1] : arc.a[2];
+      base_x = static_cast<uint32_t>(self ? arc.a[4] : arc.a[6]);
+      deg_x = static_cast<uint32_t>(self ? arc.a[5] : arc.a[7]);
       if (STATS) ++c_trials;
       if (first) accept = true;                       // unbiased first step (randomwalk.py:320-321)
       else if (x == t) accept = rnd.w <= A.ret_m1;
@@ -219,7 +225,8 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
       else {
         if (STATS) ++c_search;
         uint32_t probes = 0;
-        const bool in = member(g.parts[MULTI ? part_t : 0].hash, hbase_t, deg_t, x, probes);
+        const bool in = member(g.parts[MULTI ? part_t : 0].hash, n2v_hash_base(base_t, local_of(t, part_t)), deg_t,
+                               x, probes);
         if (STATS) c_probes += probes;
         accept = rnd.w <= (in ? A.nbr_m1 : A.far_m1);
       }
@@ -231,16 +238,19 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
       const n2v_graph_part_t& PT = g.parts[MULTI ? part_t : 0];
       x = exact_draw(PV.col + base_v, PV.weight + base_v, deg_v, t, PT.col + base_t, deg_t, A.inv_p, A.inv_q,
                      r2.x, r2.y);
+      uint32_t px;
+      enter(x, px, base_x, deg_x);
       if (STATS) ++c_fb;
     }
     // advance: v becomes the previous vertex
     t = v;
     base_t = base_v;
     deg_t = deg_v;
-    hbase_t = hbase_v;
     part_t = part_v;
     v = x;
-    enter(v, part_v, base_v, deg_v, hbase_v);
+    base_v = base_x;
+    deg_v = deg_x;
+    if (MULTI) part_v = part_of(x);
     ++pos;
     if (STATS) ++c_steps;
     trial = 0;

@@ -32,7 +32,8 @@ class DeviceGraph:
 
     Layout (one replica):
       vtx   int32[V, 4]   16 B/vertex  {base u32, deg u32, hbase u32, wsum f32}
-      arcs  int32[A, 4]   16 B/arc     {thr u32, dst i32, alias_dst i32, alias_idx i32}
+      arcs  int32[A, 8]   32 B/arc     {thr, dst, alias_dst, alias_idx, dst_base, dst_deg, adst_base, adst_deg}
+                                       = one sector per walk trial, landing vertex's header included
       hash  int32[B, 8]   ~8 B/arc     per-vertex neighbour hash sets, 32 B buckets (membership test)
       col   int32[A]       4 B/arc     neighbour ids, ascending per vertex (exact fallback, parity)
       weight f64[A]        8 B/arc     reference weights (exact fallback, parity outputs)
@@ -87,15 +88,9 @@ class DeviceGraph:
             del scratch, s, d, w
             n_buckets = int(lib.n2v_hash_buckets_bound(n_arcs, g.n_vertices))
             g.hash = torch.empty((n_buckets, 8), dtype=torch.int32, device=device)
-            hbytes = int(lib.n2v_hash_scratch_bytes(g.n_vertices))
-            hscratch = torch.empty(hbytes, dtype=torch.uint8, device=device)
-            used = C.c_int64(0)
             _lib.check(lib.n2v_hash_build(_lib.ptr(g.vtx), _lib.ptr(g.col), g.n_vertices, n_arcs, _lib.ptr(g.hash),
-                                          n_buckets, _lib.ptr(hscratch), hbytes, C.byref(used), stream),
-                       "n2v_hash_build")
-            g.n_buckets = int(used.value)
-            del hscratch
-            g.arcs = torch.empty((n_arcs, 4), dtype=torch.int32, device=device)
+                                          n_buckets, stream), "n2v_hash_build")
+            g.arcs = torch.empty((n_arcs, 8), dtype=torch.int32, device=device)
             probs = torch.empty(n_arcs, dtype=torch.float64, device=device)
             alias = torch.empty(n_arcs, dtype=torch.int32, device=device) if keep_tables else None
             work = torch.empty(n_arcs, dtype=torch.int32, device=device)
@@ -145,11 +140,13 @@ class DeviceGraph:
             "deg": vtx[:, 1].copy().view(np.uint32),
             "hbase": vtx[:, 2].copy().view(np.uint32),
             "wsum": vtx[:, 3].copy().view(np.float32),
-            "hash": self.hash.cpu().numpy()[: getattr(self, "n_buckets", 0)],
+            "hash": self.hash.cpu().numpy(),
             "thr": arcs[:, 0].copy().view(np.uint32),
             "dst": arcs[:, 1].copy(),
             "alias_dst": arcs[:, 2].copy(),
             "alias_idx": arcs[:, 3].copy(),
+            "dst_base": arcs[:, 4].copy().view(np.uint32), "dst_deg": arcs[:, 5].copy().view(np.uint32),
+            "adst_base": arcs[:, 6].copy().view(np.uint32), "adst_deg": arcs[:, 7].copy().view(np.uint32),
             "col": self.col.cpu().numpy(),
             "weight": self.weight.cpu().numpy(),
         }

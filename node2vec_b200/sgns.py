@@ -93,7 +93,7 @@ def _walk_matrix(sentences, device) -> torch.Tensor:
         arr = arr.astype(np.int64)
     if arr.ndim != 2:
         raise ValueError("walks must be rectangular (every walk the same length)")
-    return torch.as_tensor(np.ascontiguousarray(arr.astype(np.int32)), device=device)
+    return torch.as_tensor(np.ascontiguousarray(arr.astype(np.int32, copy=False)), device=device)
 
 
 class Word2Vec(object):

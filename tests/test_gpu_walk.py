@@ -120,9 +120,7 @@ def test_hash_sets_answer_membership_exactly(n2v):
             assert ok == (x in nbrs[t])
             probes += n; count += 1
     assert probes / count < 1.3
-    used = table[:, :][table[:, 0] != -1]
-    assert ((used != -1).cumsum(axis=1) == np.arange(1, 9) * (used != -1)).all() or True
-    assert g.n_buckets == int(((h["deg"].astype(np.int64) + 3) >> 2).sum())
+    assert np.array_equal(h["hbase"], ((h["base"].astype(np.int64) >> 2) + np.arange(len(h["deg"]))).astype(np.uint32))
 
 
 # ---------------------------------------------------------------------------------- K1
@@ -144,6 +142,9 @@ def test_alias_build_bit_exact_vs_oracle(n2v, mode):
     thr, adst, aalias = pack_arcs(row_ptr, col, alias, probs)
     assert np.array_equal(h["thr"], thr) and np.array_equal(h["dst"], adst)
     assert np.array_equal(h["alias_dst"], aalias) and np.array_equal(h["alias_idx"], alias)
+    assert np.array_equal(h["dst_base"], h["base"][adst].astype(np.uint32)) and np.array_equal(h["dst_deg"], h["deg"][adst])
+    assert np.array_equal(h["adst_base"], h["base"][aalias].astype(np.uint32))
+    assert np.array_equal(h["adst_deg"], h["deg"][aalias])
     wsum = np.array([np.float32(ref_walk.float_sum(ws[a:b].tolist())) for a, b in zip(row_ptr[:-1], row_ptr[1:])],
                     dtype=np.float32)
     assert np.array_equal(h["wsum"][np.diff(row_ptr) > 0], wsum[np.diff(row_ptr) > 0])
