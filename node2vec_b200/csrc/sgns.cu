@@ -128,13 +128,19 @@ __device__ __forceinline__ void add_row(float* __restrict__ base, int32_t dim, i
   }
 }
 
-__device__ __forceinline__ float sigmoid_table(const float* __restrict__ table, float f) {
-  return __ldg(table + static_cast<int>((f + kMaxExp) * (1000.0f / kMaxExp / 2.0f)));
+constexpr int kExpTable = 1000;
+
+// EXP_TABLE lookup (shared-memory copy of the host-built table; uniform index => broadcast)
+__device__ __forceinline__ float sigmoid_table(const float* table, float f) {
+  return table[static_cast<int>((f + kMaxExp) * (kExpTable / kMaxExp / 2.0f))];
 }
 
 template <int NV, bool ATOMIC>
 __global__ void __launch_bounds__(kBlock) sgns_kernel(const __grid_constant__ SgnsArgs A) {
   extern __shared__ int32_t smem[];
+  __shared__ float exp_table[kExpTable];
+  for (int i = threadIdx.x; i < kExpTable; i += kBlock) exp_table[i] = __ldg(A.exp_table + i);
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   int32_t* sent = smem + wib * A.len_cap;
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(kBlock) sgns_kernel(const __grid_constant__ Sg
         {
           const float f = dot_rows<NV>(in, pos);
           if (f > -kMaxExp && f < kMaxExp) {
-            const float g = (1.0f - sigmoid_table(A.exp_table, f)) * alpha;
+            const float g = (1.0f - sigmoid_table(exp_table, f)) * alpha;
             axpy<NV>(work, g, pos);
             update_row<NV, ATOMIC>(pos_ptr, A.dim, lane, g, in, pos);
             axpy<NV>(pos, g, in);
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(kBlock) sgns_kernel(const __grid_constant__ Sg
           const Row<NV> tr = load_row<NV>(t_ptr, A.dim, lane);
           const float f = dot_rows<NV>(in, tr);
           if (f > -kMaxExp && f < kMaxExp) {
-            const float g = (0.0f - sigmoid_table(A.exp_table, f)) * alpha;
+            const float g = (0.0f - sigmoid_table(exp_table, f)) * alpha;
             axpy<NV>(work, g, tr);
             update_row<NV, ATOMIC>(t_ptr, A.dim, lane, g, in, tr);
           } else {
