@@ -303,6 +303,18 @@ def bench_sgns(args, torch, dist, dev, world, rank, walks, w, flush, host_walks)
     }
 
 
+class _IdFrame:
+    """walk_seed stand-in: a frame with an `id` column (this rank's start vertices)."""
+
+    def __init__(self, ids):
+        import pandas as pd
+        self._df = pd.DataFrame({"id": ids})
+        self.schema = ["id"]
+
+    def as_pandas(self):
+        return self._df
+
+
 class _HostWalks:
     """A [src, walk] frame stand-in whose walk matrix is a pinned host tensor."""
 
@@ -352,20 +364,23 @@ def main():
     w = WORKLOADS[name]
     src, dst = make_graph(name)
     g = DeviceGraph.from_arcs(src, dst, None, n_vertices=w["n"])
-    start = g.start_vertices()
-    # weak scaling: rank r walks the same number of walkers, from walk numbers
-    # [r*num_walks, (r+1)*num_walks) of every start vertex (disjoint Philox streams)
-    seed = 42 + 7919 * rank
-    W = int(start.numel()) * w["num_walks"]
+    from node2vec_b200 import dist as n2v_dist
+    # weak scaling, sharded by start vertex: the N-GPU job walks num_walks * N walkers from every
+    # start vertex; rank r owns the r-th contiguous shard of the start-vertex list, so every GPU
+    # keeps ~the single-GPU walker count.  Philox is keyed by the global walk id: no collective.
+    seed = 42
+    nw = w["num_walks"] * world
+    start = n2v_dist.shard_start_vertices(g.start_vertices(), rank, world)
+    W = int(start.numel()) * nw
     steps_per_pass = W * w["walk_length"]
     pitch = (w["walk_length"] + 1 + 7) // 8 * 8
     out = torch.empty((W, pitch), dtype=torch.int32, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def one_pass():
-        g.walk(start, w["num_walks"], w["walk_length"], w["p"], w["q"], seed=seed, out=out)
+        g.walk(start, nw, w["walk_length"], w["p"], w["q"], seed=seed, out=out)
 
-    _, _, stats = g.walk(start, w["num_walks"], w["walk_length"], w["p"], w["q"], seed=seed, collect_stats=True)
+    _, _, stats = g.walk(start, nw, w["walk_length"], w["p"], w["q"], seed=seed, collect_stats=True)
     for _ in range(args.warmup):
         flush.fill_(1)
         one_pass()
@@ -388,17 +403,22 @@ def main():
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     ms_per_step = total_ms / args.steps
-    value = world * steps_per_pass / (ms_per_step * 1e-3)
+    tot_steps = torch.tensor([float(steps_per_pass)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot_steps, op=dist.ReduceOp.SUM)
+    job_steps = float(tot_steps.item())
+    value = job_steps / (ms_per_step * 1e-3)
 
     # ---- end to end through the public API, host buffers in, host walk matrix out
     src_pin = torch.as_tensor(src).pin_memory()
     dst_pin = torch.as_tensor(dst).pin_memory()
     host_out = torch.empty((W, w["walk_length"] + 1), dtype=torch.int32).pin_memory()
-    params = {"num_walks": w["num_walks"], "walk_length": w["walk_length"], "return_param": w["p"],
+    params = {"num_walks": nw, "walk_length": w["walk_length"], "return_param": w["p"],
               "inout_param": w["q"]}
+    seeds_df = _IdFrame(start.cpu().numpy()) if world > 1 else None
 
     def e2e_pass():
-        res = fugue.random_walk(None, (src_pin, dst_pin), dict(params), random_seed=seed)
+        res = fugue.random_walk(None, (src_pin, dst_pin), dict(params), seeds_df, random_seed=seed)
         host_out.copy_(res.walks_device, non_blocking=True)
         torch.cuda.synchronize()
         return res
@@ -413,7 +433,7 @@ def main():
     e2e_s = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * steps_per_pass / float(e2e_s.item())
+    e2e_value = job_steps / float(e2e_s.item())
 
     # ---- SGNS half: one epoch of skip-gram negative sampling over this rank's walk matrix
     sgns = None

@@ -22,7 +22,7 @@ from typing import Any, Dict, Optional
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, dist as n2v_dist
 
 _INT64_MAX = np.iinfo(np.int64).max
 
@@ -138,28 +138,19 @@ class Word2Vec(object):
         stream = _lib.current_stream_ptr()
         counts = torch.zeros(self._n_rows, dtype=torch.int64, device=dev)
         first = torch.full((self._n_rows,), _INT64_MAX, dtype=torch.int64, device=dev)
-        row_off = 0
-        if self.process_group is not None:
-            import torch.distributed as dist
-            sizes = [None] * dist.get_world_size(self.process_group)
-            dist.all_gather_object(sizes, (self.corpus_count, self._n_rows), group=self.process_group)
-            row_off = sum(s[0] for s in sizes[: dist.get_rank(self.process_group)])
-            self._total_walks = sum(s[0] for s in sizes)
-            n_rows = max(s[1] for s in sizes)
-            if n_rows != self._n_rows:
-                self._n_rows = n_rows
-                counts = torch.zeros(n_rows, dtype=torch.int64, device=dev)
-                first = torch.full((n_rows,), _INT64_MAX, dtype=torch.int64, device=dev)
-        else:
-            self._total_walks = self.corpus_count
+        row_off, self._total_walks, n_rows = n2v_dist.shard_layout(self.corpus_count, self._n_rows,
+                                                                   self.process_group) \
+            if self.process_group is not None else (0, self.corpus_count, self._n_rows)
+        if n_rows != self._n_rows:
+            self._n_rows = n_rows
+            counts = torch.zeros(n_rows, dtype=torch.int64, device=dev)
+            first = torch.full((n_rows,), _INT64_MAX, dtype=torch.int64, device=dev)
         self._walk_offset = row_off
         _lib.check(lib.n2v_vocab_count(_lib.ptr(walks), walks.shape[0], walks.shape[1], walks.stride(0),
                                        self._n_rows, row_off * walks.shape[1], _lib.ptr(counts), _lib.ptr(first),
                                        stream), "n2v_vocab_count")
         if self.process_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=self.process_group)
-            dist.all_reduce(first, op=dist.ReduceOp.MIN, group=self.process_group)
+            n2v_dist.reduce_vocab(counts, first, self.process_group)
         self._keep = torch.empty(self._n_rows, dtype=torch.int32, device=dev)
         self._neg = torch.empty((self._n_rows, 2), dtype=torch.int32, device=dev)
         scratch = torch.empty(self._n_rows * 12 + 64, dtype=torch.uint8, device=dev)
@@ -228,16 +219,12 @@ class Word2Vec(object):
         return st["pairs"], st["tokens_kept"]
 
     def average_tables(self) -> None:
-        """Data-parallel model averaging: NCCL sum-allreduce over NVLink, then x 1/G."""
-        import torch.distributed as dist
+        """Data-parallel model averaging: NCCL sum-allreduce over NVLink, then x 1/G (n2v_scale)."""
         lib = _lib.load()
-        G = dist.get_world_size(self.process_group)
-        for t in (self.syn0, self.syn1neg):
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.process_group)
-            if t.is_cuda:
-                _lib.check(lib.n2v_scale(_lib.ptr(t), t.numel(), 1.0 / G, _lib.current_stream_ptr()), "n2v_scale")
-            else:
-                t.mul_(1.0 / G)
+
+        def scale(t, f):
+            _lib.check(lib.n2v_scale(_lib.ptr(t), t.numel(), f, _lib.current_stream_ptr()), "n2v_scale")
+        n2v_dist.average_tables((self.syn0, self.syn1neg), self.process_group, scale)
 
     def _sync_vectors(self) -> None:
         self.wv.vectors = self.syn0[self._row_of_index].cpu().numpy()

@@ -1,0 +1,75 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU bookkeeping in node2vec_b200/dist.py:
+start-vertex sharding, shard layout, vocabulary reduction, model averaging."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from node2vec_b200 import dist as n2v_dist
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world_size, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        assert n2v_dist.world() == (rank, world_size)
+        # walks shard by start vertex
+        start = torch.arange(0, 101, dtype=torch.int32)
+        mine = n2v_dist.shard_start_vertices(start, rank, world_size)
+        # shard layout: rank r holds 10 * (r + 1) walks, sees ids up to 50 + r
+        off, total, rows = n2v_dist.shard_layout(10 * (rank + 1), 50 + rank + 1)
+        assert total == sum(10 * (r + 1) for r in range(world_size))
+        assert off == sum(10 * (r + 1) for r in range(rank)) and rows == 50 + world_size
+        # vocabulary: counts add up, first positions take the minimum
+        counts = torch.full((6,), rank + 1, dtype=torch.int64)
+        first = torch.tensor([5, 9, 1, 7, 2 ** 62, 3], dtype=torch.int64) + 100 * rank
+        n2v_dist.reduce_vocab(counts, first)
+        assert counts.tolist() == [sum(r + 1 for r in range(world_size))] * 6
+        assert first.tolist() == [5, 9, 1, 7, 2 ** 62, 3]
+        # model averaging
+        a = torch.full((4, 8), float(rank), dtype=torch.float32)
+        b = torch.arange(8, dtype=torch.float32) * (rank + 1)
+        n2v_dist.average_tables((a, b))
+        mean_rank = (world_size - 1) / 2.0
+        assert torch.allclose(a, torch.full((4, 8), mean_rank))
+        assert torch.allclose(b, torch.arange(8, dtype=torch.float32) * (mean_rank + 1))
+        np.save(os.path.join(out_dir, f"shard{rank}.npy"), mine.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_bookkeeping(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    shards = [np.load(tmp_path / f"shard{r}.npy") for r in range(2)]
+    assert np.array_equal(np.concatenate(shards), np.arange(101))      # disjoint, ordered, complete
+    assert abs(len(shards[0]) - len(shards[1])) <= 1
+
+
+def test_shard_bounds_properties():
+    for n in (0, 1, 7, 100, 1001):
+        for w in (1, 2, 3, 8):
+            b = n2v_dist.shard_bounds(n, w)
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_single_process_defaults():
+    assert n2v_dist.world() == (0, 1)
+    assert n2v_dist.shard_layout(12, 40) == (0, 12, 40)
+    t = torch.ones(3)
+    n2v_dist.average_tables((t,))
+    assert t.tolist() == [1.0, 1.0, 1.0]
