@@ -35,6 +35,10 @@ WORKLOADS = {
     # BASELINE.json configs[1] -- the largest configuration quoted on ONE B200
     "blogcatalog_like": dict(graph="blogcatalog_like(10k vertices, 334k edges)", n=10000, m=334000,
                              p=0.25, q=4.0, num_walks=80, walk_length=40, dim=128),
+    # BASELINE.json configs[2] -- power-law RMAT scale 20 (1M vertices, 16M edges): far larger than L2,
+    # the DRAM-bound regime of the same kernels
+    "rmat20": dict(graph="rmat(scale 20, edge factor 16)", n=1 << 20, m=16 << 20, p=0.25, q=4.0, num_walks=10,
+                   walk_length=80, dim=128),
     # BASELINE.json configs[0] -- the reference's own CPU-runnable case
     "er_10k": dict(graph="erdos_renyi(10k vertices, 100k edges)", n=10000, m=100000,
                    p=1.0, q=0.5, num_walks=10, walk_length=20, dim=128),
@@ -46,6 +50,12 @@ def make_graph(name):
     w = WORKLOADS[name]
     if name == "blogcatalog_like":
         return synth.blogcatalog_like(w["n"], w["m"], seed=42)
+    if name == "rmat20":
+        import torch
+        if torch.cuda.is_available():
+            src, dst = synth.rmat_device(20, 16, seed=42)
+            return src.cpu().numpy(), dst.cpu().numpy()
+        return synth.rmat_host(20, 16, seed=42)
     return synth.erdos_renyi(w["n"], w["m"], seed=42)
 
 

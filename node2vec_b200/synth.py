@@ -96,3 +96,22 @@ def rmat_device(scale: int, edge_factor: int = 16, seed: int = 42, device=None,
     lo, hi = keys >> 32, keys & 0xFFFFFFFF
     del keys
     return torch.cat([lo, hi]).to(torch.int32), torch.cat([hi, lo]).to(torch.int32)
+
+
+def rmat_host(scale: int, edge_factor: int = 16, seed: int = 42, abcd=(0.57, 0.19, 0.19, 0.05)):
+    """numpy twin of rmat_device for boxes without a GPU (CPU baseline legs)."""
+    rng = np.random.default_rng(seed)
+    n_edges = edge_factor << scale
+    a, b, c, _ = abcd
+    src = np.zeros(n_edges, dtype=np.int64)
+    dst = np.zeros(n_edges, dtype=np.int64)
+    for _ in range(scale):
+        r = rng.random(n_edges)
+        src = (src << 1) | (r >= a + b)
+        dst = (dst << 1) | (((r >= a) & (r < a + b)) | (r >= a + b + c))
+    perm = rng.permutation(1 << scale)
+    src, dst = perm[src], perm[dst]
+    lo, hi = np.minimum(src, dst), np.maximum(src, dst)
+    keys = np.unique(((lo << 32) | hi)[lo != hi])
+    lo, hi = keys >> 32, keys & 0xFFFFFFFF
+    return np.concatenate([lo, hi]).astype(np.int32), np.concatenate([hi, lo]).astype(np.int32)
