@@ -231,7 +231,7 @@ def run_reference(args):
                  "e2e": {"value": sgns_base["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0,
                          "d2h_bytes_per_step": 0}},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------
@@ -344,7 +344,30 @@ class _Col:
         return self._t.numpy()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Route fd 1 to stderr while we work (NCCL / libraries may print banners on stdout); the
+    one JSON line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -485,7 +508,7 @@ def main():
         if sgns:
             sample = host_out.numpy()
             line["sgns"]["cpu_baseline"] = cpu_baseline_sgns(sample, w["n"], w["dim"])
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

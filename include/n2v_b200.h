@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define N2V_ABI_VERSION 3
+#define N2V_ABI_VERSION 4
 #define N2V_MAX_PARTS 16
 
 /* error codes */
@@ -143,16 +143,19 @@ const char* n2v_last_error(void);
 /* ---- K0: arcs -> sorted CSR -------------------------------------------------------
  * Replaces `partition(by=["src"], presort="dst")` + get_vertex_neighbors
  * (fugue.py:130, randomwalk.py:266-275).
- * src/dst: [n_arcs] int32 ids in [0, n_vertices); weight: [n_arcs] fp64 or NULL (=1.0).
+ * src: [n_arcs] int32 ids in [0, n_vertices) (part-LOCAL ids when this is one part of a
+ * vertex-partitioned CSR); dst: ids in [0, n_dst_vertices) (always global ids;
+ * n_dst_vertices == n_vertices for a replicated graph); weight: [n_arcs] fp64 or NULL (=1.0).
+ * The SYMMETRIC flag is only computed for a replicated graph (mirrors live in other parts).
  * Out: vtx[n_vertices] (base, deg; wsum filled by n2v_alias_build), col[n_arcs],
  * weight_sorted[n_arcs], perm[n_arcs] (input position of each sorted arc; may be NULL),
  * *flags_host (N2V_GRAPH_*; this call synchronises the stream to return it).
  * Arcs are ordered by (src, dst); equal pairs keep input order (stable). */
 size_t n2v_csr_scratch_bytes(int64_t n_arcs, int64_t n_vertices);
 int n2v_csr_build(const int32_t* src, const int32_t* dst, const double* weight, int64_t n_arcs,
-                  int64_t n_vertices, n2v_vertex_t* vtx, int32_t* col, double* weight_sorted,
-                  int64_t* perm, void* scratch, size_t scratch_bytes, uint32_t* flags_host,
-                  void* stream);
+                  int64_t n_vertices, int64_t n_dst_vertices, n2v_vertex_t* vtx, int32_t* col,
+                  double* weight_sorted, int64_t* perm, void* scratch, size_t scratch_bytes,
+                  uint32_t* flags_host, void* stream);
 
 /* ---- K0b: neighbour hash sets -----------------------------------------------------
  * Replaces `set(Neighbors(src_nbs).dst_id)` (randomwalk.py:318), built once per vertex
@@ -167,14 +170,17 @@ int n2v_hash_build(n2v_vertex_t* vtx, const int32_t* col, int64_t n_vertices, in
  * Replaces generate_alias_tables (randomwalk.py:157-190) for every vertex at once (the
  * reference re-runs it per walker per step, :320-321).
  * Out: alias[n_arcs] int32 and probs[n_arcs] fp64 exactly as the reference returns them
- * per vertex (either may be NULL), arcs[n_arcs] packed records, vtx[].wsum.
+ * per vertex (alias may be NULL), arcs[n_arcs] packed records, vtx[].wsum.
+ * vtx_lookup: headers indexed by GLOBAL vertex id, read for the landing-vertex fields of the
+ * arc records; NULL = vtx itself (replicated graph).  In a vertex-partitioned CSR it is the
+ * all-gathered header array.
  * scratch: n_arcs int32 (the two LIFO work-lists share each vertex's slice).
  * *n_zero_host: number of vertices with deg > 0 whose weights sum to 0 (their tables are
  * left zeroed; the host raises).  Synchronises the stream to return it. */
-int n2v_alias_build(n2v_vertex_t* vtx, const int32_t* col, const double* weight_sorted,
-                    int64_t n_vertices, int64_t n_arcs, int sum_mode, int32_t* alias,
-                    double* probs, n2v_arc_t* arcs, int32_t* scratch, int64_t* n_zero_host,
-                    void* stream);
+int n2v_alias_build(n2v_vertex_t* vtx, const n2v_vertex_t* vtx_lookup, const int32_t* col,
+                    const double* weight_sorted, int64_t n_vertices, int64_t n_arcs, int sum_mode,
+                    int32_t* alias, double* probs, n2v_arc_t* arcs, int32_t* scratch,
+                    int64_t* n_zero_host, void* stream);
 
 /* ---- a4: second-order (p,q) alias tables for explicit (prev, cur) pairs -------------
  * Replaces generate_edge_alias_tables (randomwalk.py:193-232).  The walk kernel never
@@ -226,6 +232,18 @@ typedef struct n2v_walk_consts {
 int n2v_walk_consts(double return_param, double inout_param, uint32_t graph_flags,
                     n2v_walk_consts_t* out_host);
 
+
+/* ---- peer-shareable device buffers (vertex-partitioned CSR over NVLink) ----------------
+ * The one place the library allocates: CUDA IPC needs whole cudaMalloc allocations.  A rank
+ * allocates its part's arcs / hash / col / weight with n2v_ipc_alloc, exports a 64-byte handle
+ * per buffer, peers open it (peer access is enabled lazily by the driver) and put the mapped
+ * address into n2v_graph_t.parts[owner].  All pointers are plain device addresses. */
+#define N2V_IPC_HANDLE_BYTES 64
+int n2v_ipc_alloc(size_t bytes, void** ptr_host);
+int n2v_ipc_free(void* ptr);
+int n2v_ipc_export(const void* ptr, unsigned char* handle_host /* [64] */);
+int n2v_ipc_open(const unsigned char* handle_host /* [64] */, void** ptr_host);
+int n2v_ipc_close(void* ptr);
 
 /* ================================ SGNS half ========================================
  * Replaces gensim.models.Word2Vec(sentences=all_walks, sg=1, negative=K, ...) as called by

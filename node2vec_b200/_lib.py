@@ -45,11 +45,16 @@ _SIGNATURES = {
     "n2v_abi_version": (C.c_int, []),
     "n2v_last_error": (C.c_char_p, []),
     "n2v_csr_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
-    "n2v_csr_build": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t,
+    "n2v_csr_build": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t,
                                 C.POINTER(C.c_uint32), _P]),
+    "n2v_ipc_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "n2v_ipc_free": (C.c_int, [_P]),
+    "n2v_ipc_export": (C.c_int, [_P, C.c_char_p]),
+    "n2v_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "n2v_ipc_close": (C.c_int, [_P]),
     "n2v_hash_buckets_bound": (C.c_int64, [C.c_int64, C.c_int64]),
     "n2v_hash_build": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, C.c_int64, _P]),
-    "n2v_alias_build": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P, _P, _P,
+    "n2v_alias_build": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P, _P, _P,
                                   C.POINTER(C.c_int64), _P]),
     "n2v_edge_alias_build": (C.c_int, [C.POINTER(Graph), _P, _P, C.c_int64, C.c_double, C.c_double, C.c_int,
                                        _P, _P, _P, _P, _P]),

@@ -21,7 +21,8 @@ __device__ __forceinline__ uint32_t prob_to_thr(double pr) {
   return s >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(s);
 }
 
-__global__ void alias_build_kernel(n2v_vertex_t* __restrict__ vtx, const int32_t* __restrict__ col,
+__global__ void alias_build_kernel(n2v_vertex_t* __restrict__ vtx, const n2v_vertex_t* lookup,
+                                   const int32_t* __restrict__ col,
                                    const double* __restrict__ weight, int64_t n_vertices, int sum_mode,
                                    int32_t* __restrict__ alias, double* __restrict__ probs,
                                    n2v_arc_t* __restrict__ arcs, int32_t* __restrict__ scratch,
@@ -48,7 +49,7 @@ __global__ void alias_build_kernel(n2v_vertex_t* __restrict__ vtx, const int32_t
       for (uint32_t i = 0; i < n; ++i) {
         pr[i] = 0.0;
         const int32_t x = col[base + i];
-        out[i] = n2v_arc_t{0xFFFFFFFFu, x, x, 0, vtx[x].base, vtx[x].deg, vtx[x].base, vtx[x].deg};
+        out[i] = n2v_arc_t{0xFFFFFFFFu, x, x, 0, lookup[x].base, lookup[x].deg, lookup[x].base, lookup[x].deg};
         if (alias) alias[base + i] = 0;
       }
       continue;
@@ -63,10 +64,10 @@ __global__ void alias_build_kernel(n2v_vertex_t* __restrict__ vtx, const int32_t
       rec.alias_dst = (p >= 1.0) ? self : col[base + a];
       rec.alias_idx = a;
       // adjacency headers of both possible landing vertices (deg is final; base too: K0 ran before)
-      rec.dst_base = vtx[rec.dst].base;
-      rec.dst_deg = vtx[rec.dst].deg;
-      rec.adst_base = vtx[rec.alias_dst].base;
-      rec.adst_deg = vtx[rec.alias_dst].deg;
+      rec.dst_base = lookup[rec.dst].base;
+      rec.dst_deg = lookup[rec.dst].deg;
+      rec.adst_base = lookup[rec.alias_dst].base;
+      rec.adst_deg = lookup[rec.alias_dst].deg;
       out[i] = rec;
       if (alias) alias[base + i] = a;
     }
@@ -140,10 +141,10 @@ inline int grid_for(int64_t n) {
 
 }  // namespace
 
-extern "C" int n2v_alias_build(n2v_vertex_t* vtx, const int32_t* col, const double* weight_sorted,
-                               int64_t n_vertices, int64_t n_arcs, int sum_mode, int32_t* alias,
-                               double* probs, n2v_arc_t* arcs, int32_t* scratch, int64_t* n_zero_host,
-                               void* stream_) {
+extern "C" int n2v_alias_build(n2v_vertex_t* vtx, const n2v_vertex_t* vtx_lookup, const int32_t* col,
+                               const double* weight_sorted, int64_t n_vertices, int64_t n_arcs, int sum_mode,
+                               int32_t* alias, double* probs, n2v_arc_t* arcs, int32_t* scratch,
+                               int64_t* n_zero_host, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   N2V_CHECK_ARG(sum_mode == N2V_SUM_NAIVE || sum_mode == N2V_SUM_NEUMAIER, "n2v_alias_build: bad sum_mode %d", sum_mode);
   N2V_CHECK_ARG(n_vertices >= 0 && n_arcs >= 0, "n2v_alias_build: negative size");
@@ -153,7 +154,8 @@ extern "C" int n2v_alias_build(n2v_vertex_t* vtx, const int32_t* col, const doub
   unsigned long long* d_zero = nullptr;
   N2V_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_zero), sizeof(unsigned long long), stream));
   N2V_CUDA(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), stream));
-  alias_build_kernel<<<grid_for(n_vertices), kBlock, 0, stream>>>(vtx, col, weight_sorted, n_vertices, sum_mode,
+  alias_build_kernel<<<grid_for(n_vertices), kBlock, 0, stream>>>(vtx, vtx_lookup ? vtx_lookup : vtx, col,
+                                                                   weight_sorted, n_vertices, sum_mode,
                                                                    alias, probs, arcs, scratch, d_zero);
   N2V_LAUNCH_OK();
   unsigned long long h = 0;

@@ -19,10 +19,10 @@ inline int grid_for(int64_t n, int per_sm = 8) {
 
 __global__ void pack_keys(const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
                           int64_t n, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx,
-                          int64_t n_vertices, unsigned int* __restrict__ bad) {
+                          int64_t n_vertices, int64_t n_dst_vertices, unsigned int* __restrict__ bad) {
   for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) {
     const int32_t s = src[i], d = dst[i];
-    if (s < 0 || d < 0 || s >= n_vertices || d >= n_vertices) atomicOr(bad, 1u);
+    if (s < 0 || d < 0 || s >= n_vertices || d >= n_dst_vertices) atomicOr(bad, 1u);
     keys[i] = (static_cast<uint64_t>(static_cast<uint32_t>(s)) << 32) | static_cast<uint32_t>(d);
     idx[i] = static_cast<uint32_t>(i);
   }
@@ -114,14 +114,16 @@ extern "C" size_t n2v_csr_scratch_bytes(int64_t n_arcs, int64_t /*n_vertices*/) 
 }
 
 extern "C" int n2v_csr_build(const int32_t* src, const int32_t* dst, const double* weight,
-                             int64_t n_arcs, int64_t n_vertices, n2v_vertex_t* vtx, int32_t* col,
-                             double* weight_sorted, int64_t* perm, void* scratch,
+                             int64_t n_arcs, int64_t n_vertices, int64_t n_dst_vertices, n2v_vertex_t* vtx,
+                             int32_t* col, double* weight_sorted, int64_t* perm, void* scratch,
                              size_t scratch_bytes, uint32_t* flags_host, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   N2V_CHECK_ARG(n_arcs >= 0 && n_vertices >= 0, "n2v_csr_build: negative size");
   N2V_CHECK_ARG(n_arcs < (int64_t(1) << 32), "n2v_csr_build: %lld arcs exceed the 2^32 per-part limit",
                 static_cast<long long>(n_arcs));
-  N2V_CHECK_ARG(n_vertices <= (int64_t(1) << 31), "n2v_csr_build: vertex ids must fit int32");
+  N2V_CHECK_ARG(n_vertices <= (int64_t(1) << 31) && n_dst_vertices <= (int64_t(1) << 31) && n_dst_vertices >= 0,
+                "n2v_csr_build: vertex ids must fit int32");
+  const bool replicated = n_dst_vertices == n_vertices;
   N2V_CHECK_ARG(vtx && (n_arcs == 0 || (src && dst && col && weight_sorted && scratch)),
                 "n2v_csr_build: NULL buffer");
   const Layout L = layout_for(n_arcs);
@@ -144,11 +146,11 @@ extern "C" int n2v_csr_build(const int32_t* src, const int32_t* dst, const doubl
   N2V_CUDA(cudaMemsetAsync(dflags, 0, 256, stream));
 
   const int grid = grid_for(n_arcs);
-  pack_keys<<<grid, kBlock, 0, stream>>>(src, dst, n_arcs, keys_a, idx_a, n_vertices, dflags);
+  pack_keys<<<grid, kBlock, 0, stream>>>(src, dst, n_arcs, keys_a, idx_a, n_vertices, n_dst_vertices, dflags);
   N2V_LAUNCH_OK();
 
   int end_bit = 32;
-  while (end_bit < 64 && (int64_t(1) << (end_bit - 32)) < n_vertices) ++end_bit;
+  while (end_bit < 64 && (int64_t(1) << (end_bit - 32)) < n_vertices) ++end_bit;  // src bits; dst uses all low 32
   cub::DoubleBuffer<uint64_t> dk(keys_a, keys_b);
   cub::DoubleBuffer<uint32_t> dv(idx_a, idx_b);
   size_t cub_bytes = L.cub_bytes;
@@ -159,14 +161,18 @@ extern "C" int n2v_csr_build(const int32_t* src, const int32_t* dst, const doubl
   N2V_LAUNCH_OK();
   close_runs<<<grid, kBlock, 0, stream>>>(dk.Current(), n_arcs, vtx);
   N2V_LAUNCH_OK();
-  check_symmetric<<<grid, kBlock, 0, stream>>>(dk.Current(), weight_sorted, n_arcs, vtx, dflags + 1);
-  N2V_LAUNCH_OK();
+  if (replicated) {
+    check_symmetric<<<grid, kBlock, 0, stream>>>(dk.Current(), weight_sorted, n_arcs, vtx, dflags + 1);
+    N2V_LAUNCH_OK();
+  }
 
   unsigned int h[2] = {0, 0};
   N2V_CUDA(cudaMemcpyAsync(h, dflags, sizeof(h), cudaMemcpyDeviceToHost, stream));
   N2V_CUDA(cudaStreamSynchronize(stream));
-  N2V_CHECK_ARG(h[0] == 0, "n2v_csr_build: vertex id outside [0, %lld)", static_cast<long long>(n_vertices));
+  N2V_CHECK_ARG(h[0] == 0, "n2v_csr_build: vertex id outside [0, %lld) / [0, %lld)",
+                static_cast<long long>(n_vertices), static_cast<long long>(n_dst_vertices));
   flags &= ~h[1];
+  if (!replicated) flags &= ~uint32_t(N2V_GRAPH_SYMMETRIC);
   if (!(flags & N2V_GRAPH_SIMPLE)) flags &= ~uint32_t(N2V_GRAPH_SYMMETRIC);
   if (flags_host) *flags_host = flags;
   return N2V_OK;

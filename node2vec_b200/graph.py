@@ -81,7 +81,7 @@ class DeviceGraph:
             nbytes = int(lib.n2v_csr_scratch_bytes(n_arcs, g.n_vertices))
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
             flags = C.c_uint32(0)
-            _lib.check(lib.n2v_csr_build(_lib.ptr(s), _lib.ptr(d), _lib.ptr(w), n_arcs, g.n_vertices,
+            _lib.check(lib.n2v_csr_build(_lib.ptr(s), _lib.ptr(d), _lib.ptr(w), n_arcs, g.n_vertices, g.n_vertices,
                                          _lib.ptr(g.vtx), _lib.ptr(g.col), _lib.ptr(g.weight), _lib.ptr(g.perm),
                                          _lib.ptr(scratch), nbytes, C.byref(flags), stream), "n2v_csr_build")
             g.flags = int(flags.value)
@@ -95,7 +95,7 @@ class DeviceGraph:
             alias = torch.empty(n_arcs, dtype=torch.int32, device=device) if keep_tables else None
             work = torch.empty(n_arcs, dtype=torch.int32, device=device)
             n_zero = C.c_int64(0)
-            _lib.check(lib.n2v_alias_build(_lib.ptr(g.vtx), _lib.ptr(g.col), _lib.ptr(g.weight), g.n_vertices,
+            _lib.check(lib.n2v_alias_build(_lib.ptr(g.vtx), None, _lib.ptr(g.col), _lib.ptr(g.weight), g.n_vertices,
                                            n_arcs, _lib.SUM_MODE[sum_mode], _lib.ptr(alias), _lib.ptr(probs),
                                            _lib.ptr(g.arcs), _lib.ptr(work), C.byref(n_zero), stream),
                        "n2v_alias_build")
@@ -192,3 +192,159 @@ def walk_consts(return_param: float, inout_param: float, flags: int) -> "_lib.Wa
     c = _lib.WalkConsts()
     _lib.check(_lib.load().n2v_walk_consts(float(return_param), float(inout_param), int(flags), C.byref(c)))
     return c
+
+
+# ======================================================================================
+# Vertex-partitioned CSR: every rank owns the arcs of a contiguous vertex range; peers read
+# them over NVLink (CUDA-IPC-mapped pointers in n2v_graph_t.parts[]).
+# ======================================================================================
+class _RawBuffer(object):
+    """Zero-copy torch view of a library-allocated (IPC-shareable) device buffer."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def _ipc_tensor(lib, shape, dtype: torch.dtype, device) -> Tuple[torch.Tensor, int]:
+    typestr = {torch.int32: "<i4", torch.float64: "<f8"}[dtype]
+    n = int(np.prod(shape)) if len(shape) else 1
+    nbytes = max(n, 1) * (4 if dtype == torch.int32 else 8)
+    ptr = C.c_void_p()
+    _lib.check(lib.n2v_ipc_alloc(nbytes, C.byref(ptr)), "n2v_ipc_alloc")
+    if n == 0:
+        return torch.empty(shape, dtype=dtype, device=device), int(ptr.value)
+    return torch.as_tensor(_RawBuffer(ptr.value, shape, typestr), device=device), int(ptr.value)
+
+
+class PartitionedGraph(DeviceGraph):
+    """One rank's part of a vertex-range-partitioned graph (BASELINE configs[4]).
+
+    Rank r owns vertices [r*S, (r+1)*S), S = ceil(V / G): their arcs, alias records, hash sets
+    and weights live in ITS HBM (IPC-shareable allocations); the 16-byte vertex headers are
+    all-gathered (replicated, 16 B/vertex).  A walker started on rank r stays on rank r and
+    dereferences remote parts with plain loads through NVLink/NVSwitch -- no walker migration,
+    no collective in the walk.  Results are bit-identical to the replicated graph's.
+    """
+
+    @classmethod
+    def from_local_arcs(cls, src, dst, weight, n_vertices: int, group=None, assume_symmetric: bool = False,
+                        sum_mode: str = "naive") -> "PartitionedGraph":
+        """src/dst/weight: the arcs whose src lies in this rank's range (global ids)."""
+        import torch.distributed as dist
+        from . import dist as n2v_dist
+        _lib.require_cuda()
+        lib = _lib.load()
+        rank, G = n2v_dist.world(group)
+        if G > _lib.N2V_MAX_PARTS:
+            raise ValueError(f"at most {_lib.N2V_MAX_PARTS} parts")
+        device = torch.device("cuda", torch.cuda.current_device())
+        S = (int(n_vertices) + G - 1) // G
+        lo = rank * S
+        g = cls()
+        g.device, g.sum_mode, g.group, g.rank, g.n_parts, g.part_size = device, sum_mode, group, rank, G, S
+        g.v_lo, g.v_hi = lo, min(int(n_vertices), lo + S)
+        with torch.cuda.device(device):
+            s = _as_device_i32(src, device) - lo
+            d = _as_device_i32(dst, device)
+            w = None if weight is None else _as_device_f64(weight, device)
+            A = int(s.numel())
+            stream = _lib.current_stream_ptr()
+            g._ipc_ptrs = []
+            vtx_local = torch.zeros((S, 4), dtype=torch.int32, device=device)
+            g.col, p = _ipc_tensor(lib, (A,), torch.int32, device); g._ipc_ptrs.append(p)
+            g.weight, p = _ipc_tensor(lib, (A,), torch.float64, device); g._ipc_ptrs.append(p)
+            nbytes = int(lib.n2v_csr_scratch_bytes(A, S))
+            scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            flags = C.c_uint32(0)
+            _lib.check(lib.n2v_csr_build(_lib.ptr(s), _lib.ptr(d), _lib.ptr(w), A, S, int(n_vertices),
+                                         _lib.ptr(vtx_local), _lib.ptr(g.col), _lib.ptr(g.weight), None,
+                                         _lib.ptr(scratch), nbytes, C.byref(flags), stream), "n2v_csr_build")
+            del scratch, s, d, w
+            n_buckets = int(lib.n2v_hash_buckets_bound(A, S))
+            g.hash, p = _ipc_tensor(lib, (n_buckets, 8), torch.int32, device); g._ipc_ptrs.append(p)
+            _lib.check(lib.n2v_hash_build(_lib.ptr(vtx_local), _lib.ptr(g.col), S, A, _lib.ptr(g.hash), n_buckets,
+                                          stream), "n2v_hash_build")
+            # replicate the headers (16 B/vertex) so landing-vertex fields and walk starts are local
+            g.vtx = torch.empty((G * S, 4), dtype=torch.int32, device=device)
+            if G > 1:
+                dist.all_gather_into_tensor(g.vtx, vtx_local, group=group)
+            else:
+                g.vtx.copy_(vtx_local)
+            g.arcs, p = _ipc_tensor(lib, (A, 8), torch.int32, device); g._ipc_ptrs.append(p)
+            probs = torch.empty(A, dtype=torch.float64, device=device)
+            work = torch.empty(A, dtype=torch.int32, device=device)
+            n_zero = C.c_int64(0)
+            _lib.check(lib.n2v_alias_build(_lib.ptr(vtx_local), _lib.ptr(g.vtx), _lib.ptr(g.col), _lib.ptr(g.weight), S,
+                                           A, _lib.SUM_MODE[sum_mode], None, _lib.ptr(probs), _lib.ptr(g.arcs),
+                                           _lib.ptr(work), C.byref(n_zero), stream), "n2v_alias_build")
+            g.vtx[lo:lo + S] = vtx_local          # own wsum
+            del probs, work
+            torch.cuda.synchronize()
+            # graph-wide flags: AND over parts; symmetry cannot be checked part-locally
+            bits = (_lib.GRAPH_UNIT_WEIGHT, _lib.GRAPH_SYMMETRIC, _lib.GRAPH_SIMPLE)
+            fl = torch.tensor([1 if int(flags.value) & b else 0 for b in bits], dtype=torch.int32, device=device)
+            totals = torch.tensor([A], dtype=torch.int64, device=device)
+            if G > 1:
+                dist.all_reduce(fl, op=dist.ReduceOp.MIN, group=group)      # AND over parts
+                dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)
+            g.flags = sum(b for b, on in zip(bits, fl.tolist()) if on) & ~_lib.GRAPH_SYMMETRIC
+            if assume_symmetric and (g.flags & _lib.GRAPH_SIMPLE):
+                g.flags |= _lib.GRAPH_SYMMETRIC
+            g.n_vertices, g.n_arcs, g.n_local_arcs = int(n_vertices), int(totals.item()), A
+            # exchange IPC handles and map the peers' parts
+            handles = []
+            for t in (g.arcs, g.col, g.weight, g.hash):
+                buf = C.create_string_buffer(64)
+                ptr = [q for q in g._ipc_ptrs if q == t.data_ptr()] or [t.data_ptr()]
+                _lib.check(lib.n2v_ipc_export(C.c_void_p(ptr[0]), buf), "n2v_ipc_export")
+                handles.append(bytes(buf.raw))
+            all_handles = [None] * G
+            if G > 1:
+                dist.all_gather_object(all_handles, handles, group=group)
+            else:
+                all_handles[0] = handles
+            st = _lib.Graph()
+            st.n_vertices, st.n_arcs, st.flags = g.n_vertices, g.n_arcs, g.flags
+            st.n_parts, st.part_size = G, S
+            g._peer_ptrs = []
+            for p_idx in range(G):
+                st.parts[p_idx].vtx = g.vtx.data_ptr() + p_idx * S * 16
+                if p_idx == rank:
+                    ptrs = [g.arcs.data_ptr(), g.col.data_ptr(), g.weight.data_ptr(), g.hash.data_ptr()]
+                else:
+                    ptrs = []
+                    for h in all_handles[p_idx]:
+                        out = C.c_void_p()
+                        _lib.check(lib.n2v_ipc_open(h, C.byref(out)), "n2v_ipc_open")
+                        ptrs.append(int(out.value))
+                        g._peer_ptrs.append(int(out.value))
+                st.parts[p_idx].arcs, st.parts[p_idx].col = ptrs[0], ptrs[1]
+                st.parts[p_idx].weight, st.parts[p_idx].hash = ptrs[2], ptrs[3]
+            g._struct = st
+            if G > 1:
+                dist.barrier(group=group)
+        return g
+
+    def start_vertices(self) -> torch.Tensor:
+        """This rank's start vertices (global ids): its own range, out-degree > 0."""
+        own = self.vtx[self.v_lo:self.v_hi, 1]
+        return (torch.nonzero(own != 0).view(-1) + self.v_lo).to(torch.int32)
+
+    def nbytes(self) -> int:
+        return sum(int(t.numel()) * t.element_size() for t in (self.vtx, self.arcs, self.col, self.weight, self.hash))
+
+    def close(self) -> None:
+        """Unmap peers' parts and free this rank's shareable buffers (after a barrier)."""
+        import torch.distributed as dist
+        lib = _lib.load()
+        torch.cuda.synchronize()
+        for p in getattr(self, "_peer_ptrs", []):
+            lib.n2v_ipc_close(C.c_void_p(p))
+        self._peer_ptrs = []
+        if self.n_parts > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)
+        self.arcs = self.col = self.weight = self.hash = None
+        for p in getattr(self, "_ipc_ptrs", []):
+            lib.n2v_ipc_free(C.c_void_p(p))
+        self._ipc_ptrs = []
