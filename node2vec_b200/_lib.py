@@ -89,10 +89,10 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     path = os.environ.get("N2V_B200_LIB", _build.SO)   # override = kernel-tuning builds only
+    if path == _build.SO and build_if_missing and _build.is_stale() and _build.have_nvcc():
+        _build.build_library()          # sources newer than the .so (or no .so): rebuild in-tree
     if not os.path.exists(path):
-        if not build_if_missing or path != _build.SO:
-            raise N2VError(f"{path} is missing: run `python -m node2vec_b200.build`")
-        _build.build_library()
+        raise N2VError(f"{path} is missing: run `python -m node2vec_b200.build`")
     lib = C.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here = ABI mismatch, loudly

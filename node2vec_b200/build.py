@@ -22,15 +22,23 @@ def is_stale() -> bool:
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = sources() + [os.path.join(CSRC, "n2v_internal.cuh"),
+    deps = sources() + [os.path.join(CSRC, "n2v_internal.cuh"), os.path.join(CSRC, "alias_core.cuh"),
                         os.path.join(HERE, "..", "include", "n2v_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _nvcc() -> str:
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def have_nvcc() -> bool:
+    return os.path.exists(_nvcc())
 
 
 def build_library(force: bool = False, extra_flags=(), verbose: bool = False) -> str:
     if not force and not is_stale():
         return SO
-    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    nvcc = _nvcc()
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libn2v_b200.so")
     cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-o", SO] + sources()

@@ -13,6 +13,12 @@
 namespace {
 
 constexpr int kBlock = 128;
+// vertices with kHubMin <= deg <= kHubMax are built by one CTA each with probs / alias / work
+// lists in shared memory (16 B per arc, <= 192 KB): the sequential part then runs at
+// shared-memory latency instead of L2 latency
+constexpr uint32_t kHubMin = 256;
+constexpr uint32_t kHubMax = 12288;
+constexpr int kHubBlock = 256;
 
 __device__ __forceinline__ uint32_t prob_to_thr(double pr) {
   // u32 < thr  <=>  u32 / 2^32 < pr   (exact for pr < 1); pr >= 1 saturates (alias_dst == dst there)
@@ -26,12 +32,18 @@ __global__ void alias_build_kernel(n2v_vertex_t* __restrict__ vtx, const n2v_ver
                                    const double* __restrict__ weight, int64_t n_vertices, int sum_mode,
                                    int32_t* __restrict__ alias, double* __restrict__ probs,
                                    n2v_arc_t* __restrict__ arcs, int32_t* __restrict__ scratch,
-                                   unsigned long long* __restrict__ n_zero) {
+                                   unsigned long long* __restrict__ n_zero, int32_t* __restrict__ hubs,
+                                   unsigned int* __restrict__ n_hubs) {
   for (int64_t v = blockIdx.x * int64_t(kBlock) + threadIdx.x; v < n_vertices;
        v += int64_t(gridDim.x) * kBlock) {
     const uint64_t base = vtx[v].base;
     const uint32_t n = vtx[v].deg;
     if (n == 0) continue;
+    if (n >= kHubMin && n <= kHubMax) {  // staged in shared memory by alias_hub_kernel
+      const unsigned int slot = atomicAdd(n_hubs, 1u);
+      hubs[slot] = static_cast<int32_t>(v);
+      continue;
+    }
     double* pr = probs + base;
     n2v_arc_t* out = arcs + base;
     // left-to-right fp64 sum of the raw weights, kept as float for the weighted return-edge fold
@@ -71,6 +83,106 @@ __global__ void alias_build_kernel(n2v_vertex_t* __restrict__ vtx, const n2v_ver
       out[i] = rec;
       if (alias) alias[base + i] = a;
     }
+  }
+}
+
+// One CTA per hub vertex.  Bit-exact with the sequential reference: the fp64 sum and the LIFO
+// pairing run on thread 0 in index order; only order-free work (load, divide, pack) and the
+// order-PRESERVING list construction (chunked prefix sum) are parallel.
+__global__ void __launch_bounds__(kHubBlock)
+alias_hub_kernel(n2v_vertex_t* __restrict__ vtx, const n2v_vertex_t* lookup, const int32_t* __restrict__ col,
+                 const double* __restrict__ weight, int sum_mode, int32_t* __restrict__ alias,
+                 double* __restrict__ probs, n2v_arc_t* __restrict__ arcs, const int32_t* __restrict__ hubs,
+                 unsigned int n_hubs, unsigned long long* __restrict__ n_zero) {
+  extern __shared__ __align__(16) unsigned char hub_smem[];
+  __shared__ double s_mean;
+  __shared__ int s_counts[kHubBlock + 1];
+  __shared__ int s_ok;
+  for (unsigned int h = blockIdx.x; h < n_hubs; h += gridDim.x) {
+    const int64_t v = hubs[h];
+    const uint32_t base = vtx[v].base, n = vtx[v].deg;
+    double* pr = reinterpret_cast<double*>(hub_smem);
+    int32_t* al = reinterpret_cast<int32_t*>(pr + n);
+    int32_t* stack = al + n;
+    const int tid = threadIdx.x;
+    for (uint32_t i = tid; i < n; i += kHubBlock) {
+      pr[i] = weight[base + i];
+      al[i] = 0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double wsum = 0.0;
+      for (uint32_t i = 0; i < n; ++i) wsum = __dadd_rn(wsum, pr[i]);
+      vtx[v].wsum = static_cast<float>(wsum);
+      const double total = sum_mode == N2V_SUM_NAIVE ? wsum
+                                                     : n2v::python_sum([&](uint32_t i) { return pr[i]; }, n, sum_mode);
+      s_mean = __ddiv_rn(total, static_cast<double>(n));
+      s_ok = (s_mean != 0.0) ? 1 : 0;
+    }
+    __syncthreads();
+    const bool ok = s_ok != 0;
+    if (ok) {
+      const double mean = s_mean;
+      // probs = w / mean, then index-ordered small / large lists via a chunked prefix sum
+      const uint32_t chunk = (n + kHubBlock - 1) / kHubBlock;
+      const uint32_t lo = min(n, tid * chunk), hi = min(n, lo + chunk);
+      int n_small = 0;
+      for (uint32_t i = lo; i < hi; ++i) {
+        const double q = __ddiv_rn(pr[i], mean);
+        pr[i] = q;
+        n_small += (q < 1.0) ? 1 : 0;
+      }
+      s_counts[tid] = n_small;
+      __syncthreads();
+      if (tid == 0) {
+        int run = 0;
+        for (int t = 0; t < kHubBlock; ++t) { const int c = s_counts[t]; s_counts[t] = run; run += c; }
+        s_counts[kHubBlock] = run;
+      }
+      __syncthreads();
+      {
+        int ps = s_counts[tid];                          // smalls before this chunk
+        int pl = static_cast<int>(lo) - ps;              // larges before this chunk
+        for (uint32_t i = lo; i < hi; ++i) {
+          if (pr[i] < 1.0) stack[ps++] = static_cast<int32_t>(i);
+          else stack[n - 1 - (pl++)] = static_cast<int32_t>(i);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int64_t ns = s_counts[kHubBlock], nl = static_cast<int64_t>(n) - ns;
+        while (ns > 0 && nl > 0) {
+          const int32_t a = stack[--ns];
+          const int32_t b = stack[n - 1 - (--nl)];
+          al[a] = b;
+          const double ph = __dsub_rn(__dadd_rn(pr[b], pr[a]), 1.0);
+          pr[b] = ph;
+          if (ph < 1.0) stack[ns++] = b;
+          else stack[n - 1 - (nl++)] = b;
+        }
+      }
+      __syncthreads();
+    } else if (tid == 0) {
+      atomicAdd(n_zero, 1ull);
+    }
+    for (uint32_t i = tid; i < n; i += kHubBlock) {
+      const int32_t self = col[base + i];
+      const double p = ok ? pr[i] : 0.0;
+      const int32_t a = ok ? al[i] : 0;
+      n2v_arc_t rec;
+      rec.thr = ok ? prob_to_thr(p) : 0xFFFFFFFFu;
+      rec.dst = self;
+      rec.alias_dst = (!ok || p >= 1.0) ? self : col[base + a];
+      rec.alias_idx = a;
+      rec.dst_base = lookup[rec.dst].base;
+      rec.dst_deg = lookup[rec.dst].deg;
+      rec.adst_base = lookup[rec.alias_dst].base;
+      rec.adst_deg = lookup[rec.alias_dst].deg;
+      arcs[base + i] = rec;
+      probs[base + i] = p;
+      if (alias) alias[base + i] = a;
+    }
+    __syncthreads();
   }
 }
 
@@ -151,13 +263,29 @@ extern "C" int n2v_alias_build(n2v_vertex_t* vtx, const n2v_vertex_t* vtx_lookup
   if (n_zero_host) *n_zero_host = 0;
   if (n_arcs == 0 || n_vertices == 0) return N2V_OK;
   N2V_CHECK_ARG(vtx && col && weight_sorted && probs && arcs && scratch, "n2v_alias_build: NULL buffer");
+  // small device scratch: [0] zero-weight counter, [1] hub counter (as 2 x u32), then the hub list
+  const int64_t max_hubs = n_arcs / kHubMin + 1;
   unsigned long long* d_zero = nullptr;
-  N2V_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_zero), sizeof(unsigned long long), stream));
-  N2V_CUDA(cudaMemsetAsync(d_zero, 0, sizeof(unsigned long long), stream));
-  alias_build_kernel<<<grid_for(n_vertices), kBlock, 0, stream>>>(vtx, vtx_lookup ? vtx_lookup : vtx, col,
-                                                                   weight_sorted, n_vertices, sum_mode,
-                                                                   alias, probs, arcs, scratch, d_zero);
+  N2V_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_zero), 16 + sizeof(int32_t) * max_hubs, stream));
+  N2V_CUDA(cudaMemsetAsync(d_zero, 0, 16, stream));
+  unsigned int* d_nhubs = reinterpret_cast<unsigned int*>(d_zero + 1);
+  int32_t* d_hubs = reinterpret_cast<int32_t*>(d_zero + 2);
+  const n2v_vertex_t* lookup = vtx_lookup ? vtx_lookup : vtx;
+  alias_build_kernel<<<grid_for(n_vertices), kBlock, 0, stream>>>(vtx, lookup, col, weight_sorted, n_vertices,
+                                                                   sum_mode, alias, probs, arcs, scratch, d_zero,
+                                                                   d_hubs, d_nhubs);
   N2V_LAUNCH_OK();
+  unsigned int n_hubs = 0;
+  N2V_CUDA(cudaMemcpyAsync(&n_hubs, d_nhubs, sizeof(n_hubs), cudaMemcpyDeviceToHost, stream));
+  N2V_CUDA(cudaStreamSynchronize(stream));
+  if (n_hubs > 0) {
+    const size_t smem = static_cast<size_t>(kHubMax) * 16;
+    N2V_CUDA(cudaFuncSetAttribute(alias_hub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const unsigned int grid = n_hubs < static_cast<unsigned int>(n2v::kSmCount) ? n_hubs : n2v::kSmCount;
+    alias_hub_kernel<<<grid, kHubBlock, smem, stream>>>(vtx, lookup, col, weight_sorted, sum_mode, alias, probs,
+                                                        arcs, d_hubs, n_hubs, d_zero);
+    N2V_LAUNCH_OK();
+  }
   unsigned long long h = 0;
   N2V_CUDA(cudaMemcpyAsync(&h, d_zero, sizeof(h), cudaMemcpyDeviceToHost, stream));
   N2V_CUDA(cudaFreeAsync(d_zero, stream));

@@ -8,35 +8,46 @@ namespace {
 
 constexpr int kBlock = 128;
 
-inline int grid_for(int64_t n) {
-  const int64_t need = (n + kBlock - 1) / kBlock;
+inline int grid_for(int64_t n_warps_needed) {
+  const int64_t need = (n_warps_needed * 32 + kBlock - 1) / kBlock;
   const int64_t cap = int64_t(n2v::kSmCount) * 16;
   return static_cast<int>(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
-// one thread per vertex, sequential insertion in col[] order => deterministic layout
+// One WARP per vertex: lanes clear the vertex's buckets, then insert its arcs in parallel with
+// atomicCAS.  Slots of a bucket fill in order (a lane moves to slot k+1 only after seeing slot k
+// taken) and buckets only ever fill up, so the final table satisfies the lookup invariant "x
+// lives in the first bucket of its probe sequence that had room" whatever the interleaving.
 __global__ void fill_buckets(n2v_vertex_t* __restrict__ vtx, const int32_t* __restrict__ col,
                              int64_t n_vertices, int32_t* __restrict__ hash) {
-  for (int64_t v = blockIdx.x * int64_t(kBlock) + threadIdx.x; v < n_vertices; v += int64_t(gridDim.x) * kBlock) {
-    const uint32_t deg = vtx[v].deg, hb = n2v_hash_base(vtx[v].base, static_cast<uint32_t>(v));
-    vtx[v].hbase = hb;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * int64_t(kBlock) + threadIdx.x) >> 5;
+  const int64_t n_warps = (int64_t(gridDim.x) * kBlock) >> 5;
+  for (int64_t v = warp0; v < n_vertices; v += n_warps) {
+    const uint32_t deg = vtx[v].deg, base = vtx[v].base;
+    const uint32_t hb = n2v_hash_base(base, static_cast<uint32_t>(v));
+    if (lane == 0) vtx[v].hbase = hb;
     if (deg == 0) continue;
     const uint32_t nb = n2v_hash_nbuckets(deg);
     int32_t* table = hash + static_cast<size_t>(hb) * N2V_HASH_SLOTS;
-    for (uint32_t i = 0; i < nb * N2V_HASH_SLOTS; ++i) table[i] = N2V_HASH_EMPTY;
-    const int32_t* c = col + vtx[v].base;
-    for (uint32_t i = 0; i < deg; ++i) {
+    for (uint32_t i = lane; i < nb * N2V_HASH_SLOTS; i += 32) table[i] = N2V_HASH_EMPTY;
+    __syncwarp();
+    const int32_t* c = col + base;
+    for (uint32_t i = lane; i < deg; i += 32) {
       const int32_t x = c[i];
-      if (i > 0 && c[i - 1] == x) continue;  // multi-arc: already present (col is sorted)
+      if (i > 0 && c[i - 1] == x) continue;  // multi-arc: one entry per distinct neighbour (col is sorted)
       uint32_t b = __umulhi(static_cast<uint32_t>(x) * N2V_HASH_MULT, nb);
-      for (;;) {
+      bool done = false;
+      while (!done) {
         int32_t* slot = table + b * N2V_HASH_SLOTS;
-        int k = 0;
-        while (k < N2V_HASH_SLOTS && slot[k] != N2V_HASH_EMPTY) ++k;
-        if (k < N2V_HASH_SLOTS) { slot[k] = x; break; }
+        for (int k = 0; k < N2V_HASH_SLOTS && !done; ++k) {
+          const int32_t old = atomicCAS(slot + k, N2V_HASH_EMPTY, x);
+          done = (old == N2V_HASH_EMPTY) || (old == x);
+        }
         b = (b + 1 == nb) ? 0 : b + 1;
       }
     }
+    __syncwarp();
   }
 }
 

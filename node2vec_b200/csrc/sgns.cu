@@ -24,8 +24,10 @@ namespace {
 
 constexpr int kBlock = 256;
 constexpr int kWarps = kBlock / 32;
+#ifndef N2V_SGNS_MIN_BLOCKS
+#define N2V_SGNS_MIN_BLOCKS 4  // measured: 4 blocks (64 regs) beats 1/3 (fewer warps) and 5/6 (spills)
+#endif
 constexpr float kMaxExp = 6.0f;
-constexpr uint64_t kLcgMask = 281474976710655ULL;  // 2^48 - 1
 
 struct SgnsArgs {
   const int32_t* walks;
@@ -45,7 +47,15 @@ struct SgnsArgs {
   uint32_t key0, key1;
 };
 
-__device__ __forceinline__ uint64_t lcg_next(uint64_t r) { return (r * 25214903917ULL + 11ULL) & kLcgMask; }
+// Per-walk generator for windows and negatives: PCG-RXS-M-XS-32 (O'Neill 2014) -- one 32-bit
+// multiply-add per draw; the stream is seeded per (walk, epoch) from Philox.  (gensim uses a
+// 48-bit LCG here; any uniform source gives the same law.)
+__device__ __forceinline__ uint32_t pcg_next(uint32_t& state) {
+  const uint32_t s = state;
+  state = s * 747796405u + 2891336453u;
+  const uint32_t w = ((s >> ((s >> 28u) + 4u)) ^ s) * 277803737u;
+  return (w >> 22u) ^ w;
+}
 
 template <int NV>
 struct Row {
@@ -135,8 +145,8 @@ __device__ __forceinline__ float sigmoid_table(const float* table, float f) {
   return table[static_cast<int>((f + kMaxExp) * (kExpTable / kMaxExp / 2.0f))];
 }
 
-template <int NV, bool ATOMIC>
-__global__ void __launch_bounds__(kBlock) sgns_kernel(const __grid_constant__ SgnsArgs A) {
+template <int NV, bool ATOMIC, bool TRACE>
+__global__ void __launch_bounds__(kBlock, N2V_SGNS_MIN_BLOCKS) sgns_kernel(const __grid_constant__ SgnsArgs A) {
   extern __shared__ int32_t smem[];
   __shared__ float exp_table[kExpTable];
   for (int i = threadIdx.x; i < kExpTable; i += kBlock) exp_table[i] = __ldg(A.exp_table + i);
@@ -144,7 +154,7 @@ __global__ void __launch_bounds__(kBlock) sgns_kernel(const __grid_constant__ Sg
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   int32_t* sent = smem + wib * A.len_cap;
-  const bool tracing = A.trace != nullptr;
+  constexpr bool tracing = TRACE;
   if (tracing && (blockIdx.x != 0 || wib != 0)) return;   // trace mode: ONE warp, walks in order
   const int64_t n_warps = tracing ? 1 : static_cast<int64_t>(gridDim.x) * kWarps;
   unsigned long long c_pairs = 0, c_kept = 0, c_negskip = 0, c_clip = 0;
@@ -187,16 +197,15 @@ __global__ void __launch_bounds__(kBlock) sgns_kernel(const __grid_constant__ Sg
     }
     __syncwarp();
     c_kept += static_cast<unsigned long long>(n);
-    // per-walk 48-bit LCG (gensim's generator), seeded from Philox; identical in every lane
-    uint64_t rnd;
+    // per-walk PCG stream seeded from Philox; identical in every lane
+    uint32_t rnd;
     {
       const uint4 r = n2v::philox4x32_10(A.key0, A.key1, static_cast<uint32_t>(gs), static_cast<uint32_t>(gs >> 32),
-                                         static_cast<uint32_t>(A.epoch), 0x4C434700u);
-      rnd = ((static_cast<uint64_t>(r.y) << 32) | r.x) & kLcgMask;
+                                         static_cast<uint32_t>(A.epoch), 0x50434700u);
+      rnd = r.x;
     }
     for (int i = 0; i < n; ++i) {
-      const uint32_t b = static_cast<uint32_t>(rnd >> 16) % static_cast<uint32_t>(A.window);
-      rnd = lcg_next(rnd);
+      const uint32_t b = __umulhi(pcg_next(rnd), static_cast<uint32_t>(A.window));   // uniform on [0, window)
       int j0 = i - A.window + static_cast<int>(b), j1 = i + A.window + 1 - static_cast<int>(b);
       if (j0 < 0) j0 = 0;
       if (j1 > n) j1 = n;
@@ -213,7 +222,7 @@ __global__ void __launch_bounds__(kBlock) sgns_kernel(const __grid_constant__ Sg
 #pragma unroll
         for (int q = 0; q < NV; ++q) work.v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         int32_t* trow = nullptr;
-        if (tracing && trace_pos < A.trace_cap) {
+        if (TRACE && trace_pos < A.trace_cap) {
           trow = A.trace + trace_pos * (2 + K);
           if (lane == 0) { trow[0] = wi; trow[1] = wj; A.trace_alpha[trace_pos] = alpha; }
         }
@@ -231,19 +240,17 @@ __global__ void __launch_bounds__(kBlock) sgns_kernel(const __grid_constant__ Sg
         }
         // K negatives ~ count^0.75, one 8-byte alias gather each
         for (int d = 0; d < K; ++d) {
-          const uint32_t u1 = static_cast<uint32_t>(rnd >> 16);
-          rnd = lcg_next(rnd);
-          const uint32_t u2 = static_cast<uint32_t>(rnd >> 16);
-          rnd = lcg_next(rnd);
+          const uint32_t u1 = pcg_next(rnd);
+          const uint32_t u2 = pcg_next(rnd);
           const uint32_t slot = __umulhi(u1, A.n_vertices);
           const int2 e = __ldg(A.neg_table + slot);
           const int32_t tgt = (u2 < static_cast<uint32_t>(e.x)) ? static_cast<int32_t>(slot) : e.y;
           if (tgt == wi) {
             ++c_negskip;
-            if (trow && lane == 0) trow[2 + d] = -1;
+            if (TRACE && trow && lane == 0) trow[2 + d] = -1;
             continue;
           }
-          if (trow && lane == 0) trow[2 + d] = tgt;
+          if (TRACE && trow && lane == 0) trow[2 + d] = tgt;
           float* t_ptr = A.syn1neg + static_cast<int64_t>(tgt) * A.dim;
           const Row<NV> tr = load_row<NV>(t_ptr, A.dim, lane);
           const float f = dot_rows<NV>(in, tr);
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(kBlock) sgns_kernel(const __grid_constant__ Sg
         }
         add_row<NV, ATOMIC>(in_ptr, A.dim, lane, work, in);
         ++c_pairs;
-        if (tracing) ++trace_pos;
+        if (TRACE) ++trace_pos;
       }
     }
     __syncwarp();
@@ -272,8 +279,13 @@ __global__ void __launch_bounds__(kBlock) sgns_kernel(const __grid_constant__ Sg
 
 template <int NV>
 cudaError_t launch(const SgnsArgs& A, bool atomic, int grid, size_t smem, cudaStream_t stream) {
-  if (atomic) sgns_kernel<NV, true><<<grid, kBlock, smem, stream>>>(A);
-  else sgns_kernel<NV, false><<<grid, kBlock, smem, stream>>>(A);
+  if (A.trace) {
+    if (atomic) sgns_kernel<NV, true, true><<<grid, kBlock, smem, stream>>>(A);
+    else sgns_kernel<NV, false, true><<<grid, kBlock, smem, stream>>>(A);
+  } else {
+    if (atomic) sgns_kernel<NV, true, false><<<grid, kBlock, smem, stream>>>(A);
+    else sgns_kernel<NV, false, false><<<grid, kBlock, smem, stream>>>(A);
+  }
   return cudaGetLastError();
 }
 
@@ -345,8 +357,10 @@ extern "C" int n2v_sgns_train(const int32_t* walks, int64_t n_walks, int32_t len
 #define N2V_SGNS_LAUNCH(NVV)                                                                           \
   do {                                                                                                 \
     if (smem > 48 * 1024) {                                                                            \
-      cudaFuncSetAttribute(sgns_kernel<NVV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-      cudaFuncSetAttribute(sgns_kernel<NVV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      cudaFuncSetAttribute(sgns_kernel<NVV, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+      cudaFuncSetAttribute(sgns_kernel<NVV, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      cudaFuncSetAttribute(sgns_kernel<NVV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+      cudaFuncSetAttribute(sgns_kernel<NVV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
     }                                                                                                  \
     err = launch<NVV>(A, atomic, grid, smem, stream);                                                  \
   } while (0)

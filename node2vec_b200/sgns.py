@@ -44,9 +44,39 @@ class KeyedVectors(object):
 
     def __init__(self, vector_size: int):
         self.vector_size = vector_size
-        self.vocab: Dict[str, Vocab] = {}
-        self.index2word = []
+        self._vocab: Optional[Dict[str, Vocab]] = {}
+        self._index2word: Optional[list] = []
+        self._lazy = None       # (ids in first-appearance order, rank by count, counts, keep thresholds)
         self.vectors = np.zeros((0, vector_size), dtype=np.float32)
+
+    # The dict of Vocab objects costs ~1 us per vertex to build in Python; it is materialised on
+    # first access only (training never needs it).
+    def _materialise(self):
+        if self._lazy is not None:
+            ids, rank, counts, keep = self._lazy
+            self._lazy = None
+            self._vocab = {str(int(v)): Vocab(int(c), int(r), 2 ** 32 if k == 0xFFFFFFFF else int(k))
+                           for v, r, c, k in zip(ids.tolist(), rank.tolist(), counts.tolist(), keep.tolist())}
+            order = ids[np.argsort(rank)]
+            self._index2word = [str(int(v)) for v in order.tolist()]
+
+    @property
+    def vocab(self) -> Dict[str, Vocab]:
+        self._materialise()
+        return self._vocab
+
+    @vocab.setter
+    def vocab(self, value):
+        self._lazy, self._vocab = None, value
+
+    @property
+    def index2word(self):
+        self._materialise()
+        return self._index2word
+
+    @index2word.setter
+    def index2word(self, value):
+        self._index2word = value
 
     def __getitem__(self, token):
         if isinstance(token, (list, tuple)):
@@ -166,11 +196,8 @@ class Word2Vec(object):
         ids = ids[np.argsort(first_h[ids], kind="stable")]
         rank = np.empty(len(ids), dtype=np.int64)
         rank[np.argsort(-counts_h[ids], kind="stable")] = np.arange(len(ids))
-        self.wv.vocab = {str(int(v)): Vocab(int(counts_h[v]), int(r),
-                                            2 ** 32 if keep_h[v] == 0xFFFFFFFF else int(keep_h[v]))
-                         for v, r in zip(ids, rank)}
+        self.wv._lazy = (ids, rank, counts_h[ids], keep_h[ids])
         order = ids[np.argsort(rank)]
-        self.wv.index2word = [str(int(v)) for v in order]
         self._row_of_index = torch.as_tensor(order, device=dev)
         assert n_vocab == len(ids)
         # weights: reset_weights()
@@ -231,6 +258,7 @@ class Word2Vec(object):
 
     # ------------------------------------------------------------------ persistence
     def save(self, fname: str) -> None:
+        self.wv._materialise()
         state = {k: v for k, v in self.__dict__.items()
                  if k not in ("syn0", "syn1neg", "_keep", "_neg", "_exp", "_row_of_index", "process_group")}
         state["syn0"] = None if self.syn0 is None else self.syn0.cpu().numpy()

@@ -129,9 +129,10 @@ def test_alias_build_bit_exact_vs_oracle(n2v, mode):
     rng = np.random.default_rng(6)
     src, dst, w = _random_arcs(rng, 2000, 60000, True, False, True)
     w[rng.integers(0, len(w), 500)] = 1.0                    # exact ties / probs == 1.0 cases
-    hub = np.full(30000, 7)                                   # a 30k-degree hub
-    src = np.concatenate([src, hub]); dst = np.concatenate([dst, rng.integers(0, 2000, 30000)])
-    w = np.concatenate([w, rng.pareto(1.5, 30000) + 0.01])
+    # hubs on every build path: 255/256 (thread vs CTA boundary), 5000, 12288/12289 (CTA vs global), 30000
+    for v, deg in ((3, 255), (4, 256), (8, 5000), (9, 12288), (10, 12289), (7, 30000)):
+        src = np.concatenate([src, np.full(deg, v)]); dst = np.concatenate([dst, rng.integers(0, 2000, deg)])
+        w = np.concatenate([w, rng.pareto(1.5, deg) + 0.01])
     g = n2v.graph.DeviceGraph.from_arcs(src, dst, w, n_vertices=2000, sum_mode=mode, keep_tables=True)
     row_ptr, col, ws, _ = clib.csr_from_arcs(src, dst, w, 2000)
     alias, probs, bad = clib.alias_tables_csr(row_ptr, ws, mode, threads=4)
