@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define N2V_ABI_VERSION 4
+#define N2V_ABI_VERSION 5
 #define N2V_MAX_PARTS 16
 
 /* error codes */
@@ -112,6 +112,7 @@ typedef struct n2v_graph_part {
   const int32_t* col;       /* [part arcs] neighbour ids, ascending within a vertex */
   const double* weight;     /* [part arcs] fp64 weights in col order */
   const int32_t* hash;      /* [part buckets][8] neighbour hash sets */
+  const float* ratio;       /* [part arcs][2] {fwd, rev} return-mass ratios (n2v_ratio_build) or NULL */
 } n2v_graph_part_t;
 
 typedef struct n2v_graph {
@@ -225,12 +226,20 @@ typedef struct n2v_walk_consts {
   uint64_t t_nbr;   /* accept x in N_out(prev) iff u32 < t_nbr */
   uint64_t t_far;   /* accept otherwise      iff u32 < t_far */
   float fold_gain;  /* e' = max(0, 1/p - cap) / cap; 0 = return-edge fold off */
-  int32_t fold_mode;/* 0 off, 1 unit-weight symmetric simple graph (rho = 1/deg), 2 general */
+  int32_t fold_mode;/* 0 off, 1 unit-weight symmetric simple graph (rho = 1/deg), 2 general (per-arc ratios) */
   int32_t max_trials;
   int32_t reserved;
 } n2v_walk_consts_t;
-int n2v_walk_consts(double return_param, double inout_param, uint32_t graph_flags,
+int n2v_walk_consts(double return_param, double inout_param, uint32_t graph_flags, int has_ratio,
                     n2v_walk_consts_t* out_host);
+
+/* ---- return-mass ratios for the general (weighted / directed / multi-arc) fold ----------
+ * For arc e = (v -> x):  fwd = tot(v->x) / wsum(v),  rev = tot(x->v) / wsum(x)  (0 when x has no
+ * arc back to v), tot = left-to-right fp64 sum over the parallel arcs, cast to fp32 and divided
+ * by the fp32 vtx[].wsum.  The walk carries {fwd, rev} of the arc it took, so the probability of
+ * returning through the fold, e*rev / (1 + e*rev), needs one 8-byte gather per step and no
+ * search.  Single-part graphs; ratio_out: [n_arcs][2] fp32.  Run after n2v_alias_build. */
+int n2v_ratio_build(const n2v_graph_t* graph, float* ratio_out, void* stream);
 
 
 /* ---- peer-shareable device buffers (vertex-partitioned CSR over NVLink) ----------------

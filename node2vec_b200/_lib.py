@@ -16,7 +16,7 @@ GRAPH_UNIT_WEIGHT, GRAPH_SYMMETRIC, GRAPH_SIMPLE = 1, 2, 4
 
 class GraphPart(C.Structure):
     _fields_ = [("vtx", C.c_void_p), ("arcs", C.c_void_p), ("col", C.c_void_p), ("weight", C.c_void_p),
-                ("hash", C.c_void_p)]
+                ("hash", C.c_void_p), ("ratio", C.c_void_p)]
 
 
 class Graph(C.Structure):
@@ -61,7 +61,8 @@ _SIGNATURES = {
     "n2v_alias_draw": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P]),
     "n2v_walk": (C.c_int, [C.POINTER(Graph), _P, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_double,
                            C.c_uint64, _P, C.c_int64, _P, _P, _P]),
-    "n2v_walk_consts": (C.c_int, [C.c_double, C.c_double, C.c_uint32, C.POINTER(WalkConsts)]),
+    "n2v_walk_consts": (C.c_int, [C.c_double, C.c_double, C.c_uint32, C.c_int, C.POINTER(WalkConsts)]),
+    "n2v_ratio_build": (C.c_int, [C.POINTER(Graph), _P, _P]),
     "n2v_vocab_count": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
     "n2v_sgns_prepare": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_double, C.c_double, _P, _P, _P,
                                    C.POINTER(C.c_int64), _P]),

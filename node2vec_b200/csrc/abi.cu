@@ -34,7 +34,7 @@ static uint64_t accept_threshold(double a) {
 // alpha: 1/p back to t, 1 into N_out(t), 1/q elsewhere).  When 1/p is the only thing
 // above cap' = max(1, 1/q), its excess mass on the single return arc is drawn as a
 // separate mixture component ("fold") so the envelope stays at cap'.
-extern "C" int n2v_walk_consts(double return_param, double inout_param, uint32_t graph_flags,
+extern "C" int n2v_walk_consts(double return_param, double inout_param, uint32_t graph_flags, int has_ratio,
                                n2v_walk_consts_t* out) {
   N2V_CHECK_ARG(out != nullptr, "n2v_walk_consts: out is NULL");
   N2V_CHECK_ARG(return_param > 0.0 && inout_param > 0.0 && isfinite(return_param) &&
@@ -47,6 +47,9 @@ extern "C" int n2v_walk_consts(double return_param, double inout_param, uint32_t
   if (ip > cap) {
     if ((graph_flags & need) == need) {
       out->fold_mode = 1;
+      out->fold_gain = static_cast<float>((ip - cap) / cap);
+    } else if (has_ratio) {
+      out->fold_mode = 2;
       out->fold_gain = static_cast<float>((ip - cap) / cap);
     } else {
       cap = ip;  // no fold available: widen the envelope instead

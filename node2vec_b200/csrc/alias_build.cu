@@ -196,6 +196,34 @@ __device__ __forceinline__ bool contains_sorted(const int32_t* __restrict__ col,
   return lo < n && col[lo] == x;
 }
 
+// {fwd, rev} return-mass ratios per arc (general fold); one thread per arc
+__global__ void ratio_kernel(const n2v_vertex_t* __restrict__ vtx, const int32_t* __restrict__ col,
+                             const double* __restrict__ weight, int64_t n_vertices, float2* __restrict__ out) {
+  for (int64_t v = blockIdx.x * int64_t(kBlock) + threadIdx.x; v < n_vertices; v += int64_t(gridDim.x) * kBlock) {
+    const uint32_t base = vtx[v].base, n = vtx[v].deg;
+    const float wv = vtx[v].wsum;
+    uint32_t i = 0;
+    while (i < n) {
+      const int32_t x = col[base + i];
+      uint32_t j = i;
+      double tot = 0.0;
+      while (j < n && col[base + j] == x) tot = __dadd_rn(tot, weight[base + j++]);   // parallel arcs v -> x
+      const float fwd = __fdiv_rn(static_cast<float>(tot), wv);
+      // reverse mass: arcs x -> v (lower bound of v in x's ascending slice, then the run)
+      const uint32_t xb = vtx[x].base, xn = vtx[x].deg;
+      uint32_t lo = 0, hi = xn;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (col[xb + mid] < static_cast<int32_t>(v)) lo = mid + 1; else hi = mid;
+      }
+      double back = 0.0;
+      while (lo < xn && col[xb + lo] == static_cast<int32_t>(v)) back = __dadd_rn(back, weight[xb + lo++]);
+      const float rev = back > 0.0 ? __fdiv_rn(static_cast<float>(back), vtx[x].wsum) : 0.0f;
+      for (; i < j; ++i) out[base + i] = make_float2(fwd, rev);
+    }
+  }
+}
+
 __global__ void edge_alias_kernel(const n2v_vertex_t* __restrict__ vtx, const int32_t* __restrict__ col,
                                   const double* __restrict__ weight, const int32_t* __restrict__ prev,
                                   const int32_t* __restrict__ cur, int64_t n_pairs, double p, double q,
@@ -313,6 +341,18 @@ extern "C" int n2v_edge_alias_build(const n2v_graph_t* graph, const int32_t* pre
   edge_alias_kernel<<<grid_for(n_pairs), kBlock, 0, stream>>>(P.vtx, P.col, P.weight, prev, cur, n_pairs,
                                                               return_param, inout_param, sum_mode, out_offset,
                                                               alias_out, probs_out, scratch);
+  N2V_LAUNCH_OK();
+  return N2V_OK;
+}
+
+extern "C" int n2v_ratio_build(const n2v_graph_t* graph, float* ratio_out, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  N2V_CHECK_ARG(graph != nullptr && graph->n_parts == 1, "n2v_ratio_build: needs a single-part graph");
+  if (graph->n_arcs == 0) return N2V_OK;
+  N2V_CHECK_ARG(ratio_out != nullptr, "n2v_ratio_build: NULL buffer");
+  const n2v_graph_part_t& P = graph->parts[0];
+  ratio_kernel<<<grid_for(graph->n_vertices), kBlock, 0, stream>>>(P.vtx, P.col, P.weight, graph->n_vertices,
+                                                                  reinterpret_cast<float2*>(ratio_out));
   N2V_LAUNCH_OK();
   return N2V_OK;
 }

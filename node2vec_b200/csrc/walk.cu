@@ -85,7 +85,7 @@ __device__ bool member_sorted(const int32_t* __restrict__ col, uint32_t n, int32
 
 // Exact O(deg log deg) draw from the biased law; used only after max_trials rejections so
 // that extreme (p, q) on a hub cannot stall a lane.  Sequential fp64, no contraction.
-__device__ __noinline__ int32_t exact_draw(const int32_t* __restrict__ vcol, const double* __restrict__ vw,
+__device__ __noinline__ uint32_t exact_draw(const int32_t* __restrict__ vcol, const double* __restrict__ vw,
                                            uint32_t deg, int32_t t, const int32_t* __restrict__ tcol,
                                            uint32_t tdeg, double inv_p, double inv_q, uint32_t r0,
                                            uint32_t r1) {
@@ -101,16 +101,16 @@ __device__ __noinline__ int32_t exact_draw(const int32_t* __restrict__ vcol, con
                              1.0 / 9007199254740992.0);
   const double target = __dmul_rn(u, total);
   double run = 0.0;
-  int32_t last = vcol[deg - 1];
+  uint32_t last = deg - 1;
   for (uint32_t i = 0; i < deg; ++i) {
     const int32_t x = vcol[i];
     const double a = (x == t) ? inv_p : (member_sorted(tcol, tdeg, x) ? 1.0 : inv_q);
     const double m = __dmul_rn(vw[i], a);
     run = __dadd_rn(run, m);
-    if (m > 0.0) last = x;
-    if (target < run) return x;
+    if (m > 0.0) last = i;
+    if (target < run) return i;
   }
-  return last;
+  return last;   // index into v's arc slice
 }
 
 __device__ __forceinline__ uint32_t fold_threshold(float gain, uint32_t deg) {
@@ -119,7 +119,15 @@ __device__ __forceinline__ uint32_t fold_threshold(float gain, uint32_t deg) {
   return pr >= 1.0f ? 0xFFFFFFFFu : __float2uint_rz(__fmul_rn(pr, 4294967296.0f));
 }
 
-template <bool FOLD, bool MULTI, bool STATS>
+// general fold: P(return via fold) = e*rev / (1 + e*rev), rev = return mass / out-weight of v
+__device__ __forceinline__ uint32_t fold_threshold_ratio(float gain, float rev) {
+  const float num = __fmul_rn(gain, rev);
+  const float pr = __fdiv_rn(num, __fadd_rn(1.0f, num));
+  return pr >= 1.0f ? 0xFFFFFFFFu : __float2uint_rz(__fmul_rn(pr, 4294967296.0f));
+}
+
+// FOLD: 0 = off, 1 = unit-weight symmetric simple graph, 2 = general (per-arc {fwd, rev} ratios)
+template <int FOLD, bool MULTI, bool STATS>
 __global__ void __launch_bounds__(kBlock, kBlocksPerSm)
 walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkArgs A) {
   __shared__ int32_t stage[kStage * kBlock];  // [slot][thread]: conflict-free
@@ -134,6 +142,7 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
   uint32_t deg_t = 0, deg_v = 0, base_v = 0, base_t = 0;
   uint32_t trial = 0, thr_out = 0, wid_lo = 0, wid_hi = 0;
   uint32_t part_v = 0, part_t = 0;
+  float r_fwd = 0.f, r_rev = 0.f;   // FOLD == 2: ratios of the arc that brought the walker to v
   bool active = false;
   const int32_t L = A.walk_length;
 
@@ -204,7 +213,8 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
     bool accept;
     int32_t x;
     uint32_t base_x, deg_x;   // adjacency header of x, delivered with the proposal
-    if (FOLD && !first && rnd.x < thr_out) {
+    uint32_t arc_index = 0xFFFFFFFFu;   // part-local index of the arc taken (FOLD == 2)
+    if (FOLD != 0 && !first && rnd.x < thr_out) {
       x = t;
       base_x = base_t;
       deg_x = deg_t;
@@ -217,6 +227,7 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
       x = self ? arc.a[1] : arc.a[2];
       base_x = static_cast<uint32_t>(self ? arc.a[4] : arc.a[6]);
       deg_x = static_cast<uint32_t>(self ? arc.a[5] : arc.a[7]);
+      if (FOLD == 2) arc_index = base_v + (self ? k : static_cast<uint32_t>(arc.a[3]));
       if (STATS) ++c_trials;
       if (first) accept = true;                       // unbiased first step (randomwalk.py:320-321)
       else if (x == t) accept = rnd.w <= A.ret_m1;
@@ -236,8 +247,10 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
       const uint4 r2 = n2v::philox4x32_10(A.key0, A.key1, wid_lo, wid_hi, static_cast<uint32_t>(pos), 0xFFFFFFFFu);
       const n2v_graph_part_t& PV = g.parts[MULTI ? part_v : 0];
       const n2v_graph_part_t& PT = g.parts[MULTI ? part_t : 0];
-      x = exact_draw(PV.col + base_v, PV.weight + base_v, deg_v, t, PT.col + base_t, deg_t, A.inv_p, A.inv_q,
-                     r2.x, r2.y);
+      const uint32_t pick = exact_draw(PV.col + base_v, PV.weight + base_v, deg_v, t, PT.col + base_t, deg_t,
+                                       A.inv_p, A.inv_q, r2.x, r2.y);
+      x = PV.col[base_v + pick];
+      arc_index = base_v + pick;
       uint32_t px;
       enter(x, px, base_x, deg_x);
       if (STATS) ++c_fb;
@@ -251,6 +264,17 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
     base_v = base_x;
     deg_v = deg_x;
     if (MULTI) part_v = part_of(x);
+    if (FOLD == 2) {
+      if (arc_index != 0xFFFFFFFFu) {   // arrived through an arc: its ratios ride along
+        const float2 r = __ldg(reinterpret_cast<const float2*>(g.parts[0].ratio) + arc_index);
+        r_fwd = r.x;
+        r_rev = r.y;
+      } else {                           // arrived through the fold (back along the same arc): swap
+        const float tmp = r_fwd;
+        r_fwd = r_rev;
+        r_rev = tmp;
+      }
+    }
     ++pos;
     if (STATS) ++c_steps;
     trial = 0;
@@ -260,7 +284,8 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
       continue;
     }
     if ((pos & (kStage - 1)) == kStage - 1) flush_chunk(pos >> 3);
-    if (FOLD) thr_out = fold_threshold(A.fold_gain, deg_v);
+    if (FOLD == 1) thr_out = fold_threshold(A.fold_gain, deg_v);
+    if (FOLD == 2) thr_out = fold_threshold_ratio(A.fold_gain, r_rev);
   }
 
   if (STATS) {  // one atomic per counter per warp
@@ -289,7 +314,8 @@ extern "C" int n2v_walk(const n2v_graph_t* graph, const int32_t* start, int64_t 
                 "n2v_walk: pitch %lld must be a multiple of 8 and >= walk_length+1", static_cast<long long>(pitch));
   N2V_CHECK_ARG(n_start >= 0, "n2v_walk: negative n_start");
   n2v_walk_consts_t C;
-  const int rc = n2v_walk_consts(return_param, inout_param, graph->flags, &C);
+  const int has_ratio = (graph->n_parts == 1 && graph->parts[0].ratio != nullptr) ? 1 : 0;
+  const int rc = n2v_walk_consts(return_param, inout_param, graph->flags, has_ratio, &C);
   if (rc != N2V_OK) return rc;
   if (n_start == 0) return N2V_OK;
   N2V_CHECK_ARG(start && walks && alive, "n2v_walk: NULL buffer");
@@ -316,7 +342,7 @@ extern "C" int n2v_walk(const n2v_graph_t* graph, const int32_t* start, int64_t 
   A.inv_p = 1.0 / return_param;
   A.inv_q = 1.0 / inout_param;
 
-  const bool fold = C.fold_mode != 0;
+  const int fold = C.fold_mode;
   const bool multi = graph->n_parts > 1;
   const bool st = stats != nullptr;
   const int64_t chunk_max = int64_t(1) << 30;  // walkers per launch
@@ -330,15 +356,17 @@ extern "C" int n2v_walk(const n2v_graph_t* graph, const int32_t* start, int64_t 
     const int64_t cap = int64_t(n2v::kSmCount) * kBlocksPerSm;
     const int grid = static_cast<int>(need < cap ? need : cap);
 #define N2V_LAUNCH_WALK(F, M, S) walk_kernel<F, M, S><<<grid, kBlock, 0, stream>>>(*graph, A)
-    switch ((fold ? 4 : 0) | (multi ? 2 : 0) | (st ? 1 : 0)) {
-      case 0: N2V_LAUNCH_WALK(false, false, false); break;
-      case 1: N2V_LAUNCH_WALK(false, false, true); break;
-      case 2: N2V_LAUNCH_WALK(false, true, false); break;
-      case 3: N2V_LAUNCH_WALK(false, true, true); break;
-      case 4: N2V_LAUNCH_WALK(true, false, false); break;
-      case 5: N2V_LAUNCH_WALK(true, false, true); break;
-      case 6: N2V_LAUNCH_WALK(true, true, false); break;
-      default: N2V_LAUNCH_WALK(true, true, true); break;
+    switch (fold * 4 + (multi ? 2 : 0) + (st ? 1 : 0)) {
+      case 0: N2V_LAUNCH_WALK(0, false, false); break;
+      case 1: N2V_LAUNCH_WALK(0, false, true); break;
+      case 2: N2V_LAUNCH_WALK(0, true, false); break;
+      case 3: N2V_LAUNCH_WALK(0, true, true); break;
+      case 4: N2V_LAUNCH_WALK(1, false, false); break;
+      case 5: N2V_LAUNCH_WALK(1, false, true); break;
+      case 6: N2V_LAUNCH_WALK(1, true, false); break;
+      case 7: N2V_LAUNCH_WALK(1, true, true); break;
+      case 8: N2V_LAUNCH_WALK(2, false, false); break;
+      default: N2V_LAUNCH_WALK(2, false, true); break;   // general fold is single-part only
     }
 #undef N2V_LAUNCH_WALK
     N2V_LAUNCH_OK();

@@ -45,7 +45,7 @@ class DeviceGraph:
         self.n_arcs = 0
         self.flags = 0
         self.vtx = self.arcs = self.col = self.weight = self.hash = None
-        self.alias = self.probs = self.perm = None
+        self.alias = self.probs = self.perm = self.ratio = None
         self.device = None
         self.sum_mode = "naive"
         self._struct = None
@@ -150,10 +150,23 @@ class DeviceGraph:
             "col": self.col.cpu().numpy(),
             "weight": self.weight.cpu().numpy(),
         }
+        if self.ratio is not None:
+            out["ratio"] = self.ratio.cpu().numpy()
         if self.alias is not None:
             out["alias"] = self.alias.cpu().numpy()
             out["probs"] = self.probs.cpu().numpy()
         return out
+
+    def ensure_ratio(self) -> None:
+        """Build the per-arc {fwd, rev} return-mass ratios (general fold) once, on demand."""
+        if self.ratio is not None or self.n_arcs == 0 or self._struct.n_parts != 1:
+            return
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            self.ratio = torch.empty((self.n_arcs, 2), dtype=torch.float32, device=self.device)
+            _lib.check(lib.n2v_ratio_build(C.byref(self._struct), _lib.ptr(self.ratio), _lib.current_stream_ptr()),
+                       "n2v_ratio_build")
+            self._struct.parts[0].ratio = self.ratio.data_ptr()
 
     # ------------------------------------------------------------------ K2
     def walk(self, start, num_walks: int, walk_length: int, return_param: float = 1.0,
@@ -166,6 +179,9 @@ class DeviceGraph:
             raise ValueError(f"Zero return ({return_param}) or inout ({inout_param}) parameter!")
         if seed is None:
             seed = int.from_bytes(os.urandom(8), "little")
+        need = _lib.GRAPH_UNIT_WEIGHT | _lib.GRAPH_SYMMETRIC | _lib.GRAPH_SIMPLE
+        if (self.flags & need) != need and 1.0 / return_param > max(1.0, 1.0 / inout_param):
+            self.ensure_ratio()      # weighted / directed / multi-arc graph with small p: general fold
         with torch.cuda.device(self.device):
             start_t = _as_device_i32(start, self.device)
             n_start = int(start_t.numel())
@@ -187,10 +203,11 @@ class DeviceGraph:
         return out[:, : walk_length + 1], alive.bool(), st
 
 
-def walk_consts(return_param: float, inout_param: float, flags: int) -> "_lib.WalkConsts":
+def walk_consts(return_param: float, inout_param: float, flags: int, has_ratio: bool = False) -> "_lib.WalkConsts":
     """Host-only: the sampling constants n2v_walk will use (no GPU needed)."""
     c = _lib.WalkConsts()
-    _lib.check(_lib.load().n2v_walk_consts(float(return_param), float(inout_param), int(flags), C.byref(c)))
+    _lib.check(_lib.load().n2v_walk_consts(float(return_param), float(inout_param), int(flags),
+                                           1 if has_ratio else 0, C.byref(c)))
     return c
 
 

@@ -156,16 +156,40 @@ def philox(key, ctr):
     return list(o)
 
 
-def walk_consts(p, q, graph_flags):
+def walk_consts(p, q, graph_flags, has_ratio=False):
     lib = load()
     c = WalkConsts()
-    if lib.orc_walk_consts_for(C.c_double(p), C.c_double(q), C.c_uint32(graph_flags), C.byref(c)) != 0:
+    if lib.orc_walk_consts_for(C.c_double(p), C.c_double(q), C.c_uint32(graph_flags), C.c_int(1 if has_ratio else 0),
+                               C.byref(c)) != 0:
         raise ValueError(f"Zero return ({p}) or inout ({q}) parameter!")
     return c
 
 
+def return_ratios(row_ptr, col, weight):
+    """{fwd, rev} per arc as include/n2v_b200.h defines them for the general fold (small graphs:
+    plain Python loops, sequential fp64 sums, fp32 division)."""
+    n = len(row_ptr) - 1
+    wsum = np.zeros(n, dtype=np.float32)
+    tot = {}
+    for v in range(n):
+        s = 0.0
+        for e in range(row_ptr[v], row_ptr[v + 1]):
+            s = s + float(weight[e])
+            key = (v, int(col[e]))
+            tot[key] = tot.get(key, 0.0) + float(weight[e])
+        wsum[v] = np.float32(s)
+    out = np.zeros((len(col), 2), dtype=np.float32)
+    for v in range(n):
+        for e in range(row_ptr[v], row_ptr[v + 1]):
+            x = int(col[e])
+            out[e, 0] = np.float32(tot[(v, x)]) / wsum[v]
+            back = tot.get((x, v), 0.0)
+            out[e, 1] = np.float32(back) / wsum[x] if back > 0.0 else np.float32(0.0)
+    return out
+
+
 def replay_walk(base, deg, arc_thr, arc_dst, arc_alias_dst, col, weight, graph_flags, p, q, start,
-                num_walks, walk_length, seed, pitch=None, threads=1):
+                num_walks, walk_length, seed, pitch=None, threads=1, alias_idx=None, ratio=None):
     """Host replay of the device sampler (bit-exact twin of n2v_walk)."""
     lib = load()
     base = np.ascontiguousarray(base, dtype=np.uint64)
@@ -181,15 +205,19 @@ def replay_walk(base, deg, arc_thr, arc_dst, arc_alias_dst, col, weight, graph_f
     W = len(start) * num_walks
     walks = np.empty((W, pitch), dtype=np.int32)
     alive = np.empty(W, dtype=np.uint8)
-    consts = walk_consts(p, q, graph_flags)
+    consts = walk_consts(p, q, graph_flags, ratio is not None)
     stats = np.zeros((threads, 8), dtype=np.uint64)
+    alias_idx = np.zeros(len(col), dtype=np.int32) if alias_idx is None else np.ascontiguousarray(alias_idx, dtype=np.int32)
+    ratio_arr = None if ratio is None else np.ascontiguousarray(ratio, dtype=np.float32)
+    ratio_ptr = C.c_void_p(0) if ratio_arr is None else ratio_arr.ctypes.data_as(C.c_void_p)
 
     def run(i):
         lo, hi = W * i // threads, W * (i + 1) // threads
         st = stats[i]
         lib.orc_replay_walk(
             _ptr(base, C.c_uint64), _ptr(deg, C.c_uint32), _ptr(arc_thr, C.c_uint32), _ptr(arc_dst, C.c_int32),
-            _ptr(arc_alias_dst, C.c_int32), _ptr(col, C.c_int32), _ptr(weight, C.c_double), C.byref(consts),
+            _ptr(arc_alias_dst, C.c_int32), _ptr(alias_idx, C.c_int32), ratio_ptr, _ptr(col, C.c_int32),
+            _ptr(weight, C.c_double), C.byref(consts),
             C.c_double(p), C.c_double(q), _ptr(start, C.c_int32), C.c_int64(len(start)), C.c_int32(num_walks),
             C.c_int32(walk_length), C.c_uint64(seed), C.c_int64(lo), C.c_int64(hi), _ptr(walks, C.c_int32),
             C.c_int64(pitch), _ptr(alive, C.c_uint8), _ptr(st, C.c_uint64))

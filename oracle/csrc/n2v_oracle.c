@@ -308,13 +308,14 @@ static uint64_t accept_thr(double a) {
 
 /* envelope and fold constants: rejection sampling of w(v,x)*alpha(t,x) from the
  * first-order table; graph_flags bit0 unit weights, bit1 symmetric, bit2 simple */
-int orc_walk_consts_for(double p, double q, uint32_t graph_flags, orc_walk_consts* c) {
+int orc_walk_consts_for(double p, double q, uint32_t graph_flags, int has_ratio, orc_walk_consts* c) {
   if (!(p > 0.0) || !(q > 0.0) || !isfinite(p) || !isfinite(q)) return -1;
   const double ip = 1.0 / p, iq = 1.0 / q;
   double cap = iq > 1.0 ? iq : 1.0;
   memset(c, 0, sizeof(*c));
   if (ip > cap) {
     if ((graph_flags & 7u) == 7u) { c->fold_mode = 1; c->fold_gain = (float)((ip - cap) / cap); }
+    else if (has_ratio) { c->fold_mode = 2; c->fold_gain = (float)((ip - cap) / cap); }
     else cap = ip;
   }
   c->t_ret = accept_thr((ip < cap ? ip : cap) / cap);
@@ -336,8 +337,8 @@ static int member_probe(const int32_t* col, uint32_t n, int32_t x, uint64_t* pro
   return col[lo] == x;
 }
 
-static int32_t exact_draw(const int32_t* vcol, const double* vw, uint32_t deg, int32_t t, const int32_t* tcol,
-                          uint32_t tdeg, double inv_p, double inv_q, uint32_t r0, uint32_t r1, uint64_t* probes) {
+static uint32_t exact_draw(const int32_t* vcol, const double* vw, uint32_t deg, int32_t t, const int32_t* tcol,
+                           uint32_t tdeg, double inv_p, double inv_q, uint32_t r0, uint32_t r1, uint64_t* probes) {
   double total = 0.0;
   for (uint32_t i = 0; i < deg; ++i) {
     const int32_t x = vcol[i];
@@ -347,16 +348,16 @@ static int32_t exact_draw(const int32_t* vcol, const double* vw, uint32_t deg, i
   const double u = ((double)(r0 >> 5) * 67108864.0 + (double)(r1 >> 6)) * (1.0 / 9007199254740992.0);
   const double target = u * total;
   double run = 0.0;
-  int32_t last = vcol[deg - 1];
+  uint32_t last = deg - 1;
   for (uint32_t i = 0; i < deg; ++i) {
     const int32_t x = vcol[i];
     const double a = (x == t) ? inv_p : (member_probe(tcol, tdeg, x, probes) ? 1.0 : inv_q);
     const double m = vw[i] * a;
     run = run + m;
-    if (m > 0.0) last = x;
-    if (target < run) return x;
+    if (m > 0.0) last = i;
+    if (target < run) return i;
   }
-  return last;
+  return last; /* index into v's arc slice */
 }
 
 /*
@@ -366,7 +367,8 @@ static int32_t exact_draw(const int32_t* vcol, const double* vw, uint32_t deg, i
  * (added into; a caller running ranges on several threads passes one stats[] per thread).
  */
 int orc_replay_walk(const uint64_t* base, const uint32_t* deg, const uint32_t* arc_thr, const int32_t* arc_dst,
-                    const int32_t* arc_alias_dst, const int32_t* col, const double* weight,
+                    const int32_t* arc_alias_dst, const int32_t* arc_alias_idx, const float* ratio /* [A][2] or NULL */,
+                    const int32_t* col, const double* weight,
                     const orc_walk_consts* c, double p, double q, const int32_t* start, int64_t n_start,
                     int32_t num_walks, int32_t walk_length, uint64_t seed, int64_t w_lo, int64_t w_hi,
                     int32_t* walks, int64_t pitch, uint8_t* alive, uint64_t* stats) {
@@ -385,6 +387,7 @@ int orc_replay_walk(const uint64_t* base, const uint32_t* deg, const uint32_t* a
     const uint64_t walk_id = (uint64_t)(uint32_t)v * (uint32_t)num_walks + (uint64_t)(w % num_walks);
     row[0] = v;
     uint8_t ok = 1;
+    float r_fwd = 0.0f, r_rev = 0.0f; /* general fold: ratios of the arc that brought us to v */
     for (int32_t pos = 0; pos < walk_length; ++pos) {
       const uint32_t dv = deg[v];
       if (dv == 0) { ok = 0; ++st[6]; break; }
@@ -392,16 +395,23 @@ int orc_replay_walk(const uint64_t* base, const uint32_t* deg, const uint32_t* a
       if (c->fold_mode == 1 && pos > 0) {
         const float pr = c->fold_gain / ((float)dv + c->fold_gain);
         thr_out = pr >= 1.0f ? 0xFFFFFFFFu : (uint32_t)(pr * 4294967296.0f);
+      } else if (c->fold_mode == 2 && pos > 0) {
+        const float num = c->fold_gain * r_rev;
+        const float pr = num / (1.0f + num);
+        thr_out = pr >= 1.0f ? 0xFFFFFFFFu : (uint32_t)(pr * 4294967296.0f);
       }
       int32_t x = -1;
       int accepted = 0;
+      int64_t arc_index = -1;
       for (uint32_t trial = 0; trial < (uint32_t)c->max_trials; ++trial) {
         const uint32_t ctr[4] = {(uint32_t)walk_id, (uint32_t)(walk_id >> 32), (uint32_t)pos, trial};
         uint32_t r[4];
         philox4x32_10(k0, k1, ctr, r);
-        if (c->fold_mode == 1 && pos > 0 && r[0] < thr_out) { x = t; accepted = 1; ++st[4]; break; }
+        if (c->fold_mode != 0 && pos > 0 && r[0] < thr_out) { x = t; accepted = 1; arc_index = -1; ++st[4]; break; }
         const uint64_t e = base[v] + (uint64_t)(((uint64_t)r[1] * dv) >> 32);
-        x = r[2] < arc_thr[e] ? arc_dst[e] : arc_alias_dst[e];
+        const int self = r[2] < arc_thr[e];
+        x = self ? arc_dst[e] : arc_alias_dst[e];
+        arc_index = self ? (int64_t)e : (int64_t)(base[v] + (uint64_t)arc_alias_idx[e]);
         ++st[1];
         if (pos == 0) accepted = 1;
         else if (x == t) accepted = r[3] <= ret_m1;
@@ -417,8 +427,15 @@ int orc_replay_walk(const uint64_t* base, const uint32_t* deg, const uint32_t* a
         const uint32_t ctr[4] = {(uint32_t)walk_id, (uint32_t)(walk_id >> 32), (uint32_t)pos, 0xFFFFFFFFu};
         uint32_t r[4];
         philox4x32_10(k0, k1, ctr, r);
-        x = exact_draw(col + base[v], weight + base[v], dv, t, col + base[t], deg[t], inv_p, inv_q, r[0], r[1], &st[2]);
+        const uint32_t pick = exact_draw(col + base[v], weight + base[v], dv, t, col + base[t], deg[t], inv_p, inv_q,
+                                         r[0], r[1], &st[2]);
+        x = col[base[v] + pick];
+        arc_index = (int64_t)(base[v] + pick);
         ++st[5];
+      }
+      if (c->fold_mode == 2) {
+        if (arc_index >= 0) { r_fwd = ratio[2 * arc_index]; r_rev = ratio[2 * arc_index + 1]; }
+        else { const float tmp = r_fwd; r_fwd = r_rev; r_rev = tmp; }
       }
       t = v;
       v = x;

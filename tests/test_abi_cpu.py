@@ -33,9 +33,9 @@ def test_header_symbols_exported(lib):
 
 def test_abi_version_and_struct_sizes(lib):
     from node2vec_b200 import _lib
-    assert lib.n2v_abi_version() == 4
-    assert C.sizeof(_lib.GraphPart) == 40
-    assert C.sizeof(_lib.Graph) == 8 + 8 + 4 + 4 + 8 + 40 * 16
+    assert lib.n2v_abi_version() == 5
+    assert C.sizeof(_lib.GraphPart) == 48
+    assert C.sizeof(_lib.Graph) == 8 + 8 + 4 + 4 + 8 + 48 * 16
     assert C.sizeof(_lib.WalkConsts) == 40
 
 
@@ -43,8 +43,8 @@ def test_walk_consts_host_only(lib):
     from node2vec_b200 import graph
     from oracle import clib
     for p, q in [(1.0, 1.0), (1.0, 0.5), (0.25, 4.0), (4.0, 0.25), (0.5, 0.5), (1e-3, 1e3), (3.0, 7.0)]:
-        for flags in (0, 7, 3, 5):
-            a, b = graph.walk_consts(p, q, flags), clib.walk_consts(p, q, flags)
+        for flags, ratio in ((0, False), (7, False), (3, False), (5, True), (0, True)):
+            a, b = graph.walk_consts(p, q, flags, ratio), clib.walk_consts(p, q, flags, ratio)
             assert (a.t_ret, a.t_nbr, a.t_far, a.fold_mode, a.max_trials) == \
                    (b.t_ret, b.t_nbr, b.t_far, b.fold_mode, b.max_trials)
             assert a.fold_gain == b.fold_gain
@@ -55,6 +55,8 @@ def test_walk_consts_host_only(lib):
     assert c.fold_mode == 1 and c.t_nbr == 2 ** 32 and c.t_far == 2 ** 30 and abs(c.fold_gain - 3.0) < 1e-6
     c = graph.walk_consts(0.25, 4.0, 0)                     # no fold possible: envelope 1/p = 4
     assert c.fold_mode == 0 and c.t_ret == 2 ** 32 and c.t_nbr == 2 ** 30 and c.t_far == 2 ** 28
+    c = graph.walk_consts(0.25, 4.0, 0, True)               # general fold through per-arc ratios
+    assert c.fold_mode == 2 and c.t_nbr == 2 ** 32 and c.t_far == 2 ** 30 and abs(c.fold_gain - 3.0) < 1e-6
     with pytest.raises(ValueError):
         graph.walk_consts(0.0, 1.0, 0)
     with pytest.raises(ValueError):

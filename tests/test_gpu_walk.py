@@ -285,8 +285,14 @@ def test_whole_reference_walks_through_row_facade(n2v):
 # ---------------------------------------------------------------------------------- K2
 def _replay(g, p, q, start, num_walks, L, seed, threads=4):
     h = g.to_host()
+    ratio = None
+    if g.ratio is not None:      # general fold in use: ratios recomputed independently on the host
+        row_ptr = np.concatenate([[0], np.cumsum(h["deg"].astype(np.int64))])
+        ratio = clib.return_ratios(row_ptr, h["col"], h["weight"])
+        assert np.array_equal(ratio.view(np.uint32), h["ratio"].view(np.uint32))
     return clib.replay_walk(h["base"], h["deg"], h["thr"], h["dst"], h["alias_dst"], h["col"], h["weight"],
-                            g.flags, p, q, start, num_walks, L, seed, threads=threads)
+                            g.flags, p, q, start, num_walks, L, seed, threads=threads, alias_idx=h["alias_idx"],
+                            ratio=ratio)
 
 
 WALK_CASES = [
@@ -294,7 +300,8 @@ WALK_CASES = [
     (300, 3000, True, False, True, 1.0, 1.0, 3, 9),
     (300, 3000, False, True, False, 1.0, 0.5, 4, 20),
     (300, 3000, False, True, False, 0.25, 4.0, 4, 40),      # fold path
-    (300, 3000, True, True, False, 0.25, 4.0, 2, 17),       # weighted: no fold, wide envelope
+    (300, 3000, True, True, False, 0.25, 4.0, 2, 17),       # weighted symmetric: general fold (per-arc ratios)
+    (300, 3000, True, False, True, 0.2, 1.0, 3, 25),         # weighted directed multi-arc: general fold, sinks
     (300, 2000, True, False, False, 4.0, 0.25, 2, 8),       # directed with sinks
     (50, 400, False, True, False, 100.0, 1000.0, 6, 5),      # fallback scans
     (2000, 40000, False, True, False, 0.5, 2.0, 2, 80),
@@ -307,8 +314,9 @@ def test_walk_equals_host_replay(n2v, case):
     rng = np.random.default_rng(hash(case) % 2 ** 31)
     src, dst, w = _random_arcs(rng, n, m, weighted, sym, multi)
     g = n2v.graph.DeviceGraph.from_arcs(src, dst, w if weighted else None, n_vertices=n + 3)
-    consts = n2v.graph.walk_consts(p, q, g.flags)
-    oc = clib.walk_consts(p, q, g.flags)
+    need_ratio = (g.flags & 7) != 7 and 1.0 / p > max(1.0, 1.0 / q)
+    consts = n2v.graph.walk_consts(p, q, g.flags, need_ratio)
+    oc = clib.walk_consts(p, q, g.flags, need_ratio)
     assert (consts.t_ret, consts.t_nbr, consts.t_far, consts.fold_mode, consts.max_trials) == \
         (oc.t_ret, oc.t_nbr, oc.t_far, oc.fold_mode, oc.max_trials)
     assert np.float32(consts.fold_gain) == np.float32(oc.fold_gain)
@@ -326,6 +334,8 @@ def test_walk_equals_host_replay(n2v, case):
     assert n2v.torch.equal(walks, walks2) and n2v.torch.equal(alive, alive2)
     if case[5] == 0.25 and not weighted:
         assert consts.fold_mode == 1 and stats["fold_hits"] > 0
+    if need_ratio:
+        assert consts.fold_mode == 2 and g.ratio is not None and stats["fold_hits"] > 0
     if p == 100.0:
         assert stats["fallbacks"] > 0
     if not sym:

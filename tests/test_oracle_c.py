@@ -110,11 +110,12 @@ def _second_order_counts(walks, alive, pos):
     return out
 
 
-@pytest.mark.parametrize("p,q,weighted,sym", [
-    (1.0, 1.0, True, False), (1.0, 0.5, False, True), (0.25, 4.0, False, True),
-    (4.0, 0.25, True, True), (0.25, 4.0, True, False), (0.5, 2.0, False, False),
+@pytest.mark.parametrize("p,q,weighted,sym,use_ratio", [
+    (1.0, 1.0, True, False, False), (1.0, 0.5, False, True, False), (0.25, 4.0, False, True, False),
+    (4.0, 0.25, True, True, False), (0.25, 4.0, True, False, False), (0.5, 2.0, False, False, False),
+    (0.25, 4.0, True, False, True), (0.2, 1.0, True, True, True), (0.5, 2.0, False, False, True),
 ])
-def test_replay_draws_from_reference_law(p, q, weighted, sym):
+def test_replay_draws_from_reference_law(p, q, weighted, sym, use_ratio):
     rng = np.random.default_rng(11)
     n = 12
     pairs = {(int(a), int(b)) for a, b in rng.integers(0, n, (60, 2)) if a != b}
@@ -132,8 +133,14 @@ def test_replay_draws_from_reference_law(p, q, weighted, sym):
     consts = clib.walk_consts(p, q, flags)
     assert (consts.fold_mode == 1) == (p < min(1.0, q) and not weighted and sym)
     starts = np.flatnonzero(np.diff(row_ptr) > 0).astype(np.int32)
+    ratio = alias_idx = None
+    if use_ratio:
+        alias_idx, _, _ = clib.alias_tables_csr(row_ptr, ws)
+        ratio = clib.return_ratios(row_ptr, col, ws)
+        c2 = clib.walk_consts(p, q, flags, True)
+        assert c2.fold_mode == (2 if (p < min(1.0, q) and consts.fold_mode == 0) else consts.fold_mode)
     walks, alive, stats = clib.replay_walk(row_ptr[:-1], np.diff(row_ptr), thr, adst, aalias, col, ws, flags,
-                                           p, q, starts, 6000, 3, seed=1234)
+                                           p, q, starts, 6000, 3, seed=1234, alias_idx=alias_idx, ratio=ratio)
     adj = ref_walk.build_adjacency(src, dst, w)
     # first step: unbiased law
     for v in starts[:4]:
