@@ -124,6 +124,17 @@ def trim_index(
     (fugue.py:24-77): ``max_out_deg <= 0`` means 100000 (randomwalk.py:254-255);
     ``indexed=True`` returns the trimmed frame untouched and ``None``."""
     logging.info("trim_index(): start validating, trimming, and indexing ...")
+    if isinstance(df_graph, (tuple, list)) and len(df_graph) in (2, 3) and isinstance(df_graph[0], torch.Tensor):
+        # integer-id arc tensors (graphs too large for pandas): device-side trimming / symmetrising
+        from .preprocess import symmetrise_device, trim_hotspots_device
+        if indexed is not True:
+            raise ValueError("tensor inputs must already be indexed (integer vertex ids): pass indexed=True")
+        src, dst = df_graph[0], df_graph[1]
+        w = df_graph[2] if len(df_graph) == 3 else None
+        if directed is not True:
+            src, dst, w = symmetrise_device(src, dst, w)
+        src, dst, w = trim_hotspots_device(src, dst, w, max_out_deg, random_seed)
+        return ((src, dst) if w is None else (src, dst, w)), None
     cols = _columns(df_graph)
     if "src" not in cols or "dst" not in cols:
         raise ValueError(f"Input graph NOT in the right format: {cols}")

@@ -499,3 +499,74 @@ def test_full_size_properties_config2(n2v):
     assert torch.equal(sub, walks[100 * 80:140 * 80])
     rw, ra, rs = _replay(g, 0.25, 4.0, start[:50].cpu().numpy(), 80, 40, 42)
     assert np.array_equal(rw[:, :41], walks[:50 * 80].cpu().numpy())
+
+
+def test_device_trim_and_symmetrise(n2v):
+    """preprocess.py on tensors: the reference's trimming law and undirected expansion."""
+    torch = n2v.torch
+    from node2vec_b200 import preprocess
+    rng = np.random.default_rng(12)
+    src = np.concatenate([rng.integers(0, 50, 400), np.full(5000, 7), np.full(300, 9)])
+    dst = rng.integers(0, 6000, len(src))
+    w = rng.uniform(0.1, 2.0, len(src))
+    ts, td, tw = (torch.as_tensor(x, device="cuda") for x in (src, dst, w))
+    s2, d2, w2 = preprocess.trim_hotspots_device(ts, td, tw, max_out_deg=100, seed=3)
+    deg = np.bincount(s2.cpu().numpy(), minlength=50)
+    want = np.minimum(np.bincount(src, minlength=50), 100)
+    assert deg.tolist() == want.tolist()
+    kept = set(zip(s2.cpu().tolist(), d2.cpu().tolist(), w2.cpu().tolist()))
+    assert kept <= set(zip(src.tolist(), dst.tolist(), w.tolist()))           # a sub-multiset of the input
+    a = preprocess.trim_hotspots_device(ts, td, tw, 100, seed=3)[1]
+    b = preprocess.trim_hotspots_device(ts, td, tw, 100, seed=4)[1]
+    assert torch.equal(a, d2) and not torch.equal(a, b)                        # seeded
+    # uniformity of the sample: each of vertex 7's 5000 arcs survives with probability 100/5000
+    pos7 = np.flatnonzero(src == 7)
+    hits = np.zeros(len(pos7))
+    for seed in range(60):
+        keep_d = preprocess.trim_hotspots_device(ts[pos7], td[pos7], tw[pos7], 100, seed=seed)[2].cpu().numpy()
+        hits += np.isin(w[pos7], keep_d)
+    assert abs(hits.mean() - 60 * 100 / len(pos7)) < 1e-9 and hits.max() <= 12 and (hits > 0).mean() > 0.6
+    # pass-through and the reference's "<= 0 means 100000"
+    assert preprocess.trim_hotspots_device(ts, td, tw, 0)[0].numel() == len(src)
+    # symmetrise: same triples as the pandas indexer's undirected expansion
+    import pandas as pd
+    from node2vec_b200.indexer import index_graph_pandas
+    g = pd.DataFrame({"src": [0, 1, 2, 2, 3], "dst": [1, 0, 3, 3, 2], "weight": [1.0, 1.0, 0.5, 0.5, 0.7]})
+    e, _ = index_graph_pandas(g.copy(), False)
+    s3, d3, w3 = preprocess.symmetrise_device(*(torch.as_tensor(g[c].to_numpy(), device="cuda") for c in ("src", "dst", "weight")))
+    # ids here are already 0..3 and first-occurrence order maps them to themselves except none: compare as sets
+    name = {v: k for k, v in enumerate([0, 1, 2, 3])}
+    assert set(zip(s3.cpu().tolist(), d3.cpu().tolist(), w3.cpu().tolist())) == \
+        set(zip(g["src"].tolist() + g["dst"].tolist(), g["dst"].tolist() + g["src"].tolist(), g["weight"].tolist() * 2))
+    assert len(s3) == len(e)
+    out, none = n2v.fugue.trim_index(None, (ts, td, tw), indexed=True, directed=True, max_out_deg=100, random_seed=3)
+    assert none is None and torch.equal(out[1], d2)
+
+
+def test_full_size_properties_config3(n2v):
+    """BASELINE configs[2] shape: RMAT scale 20 with 16 injected hotspots of degree 2^18, trimmed to
+    max_out_deg = 10000 on the device, 10 walks x 80.  The trimmed graph is directed (hotspots keep
+    10k out-arcs but all their in-arcs), so this exercises the general fold at scale."""
+    torch = n2v.torch
+    from node2vec_b200 import synth
+    src, dst = synth.rmat_device(20, 16, seed=42, hotspots=16, hotspot_degree=1 << 18)
+    (src, dst), _ = n2v.fugue.trim_index(None, (src, dst), indexed=True, directed=True, max_out_deg=10000,
+                                         random_seed=1)
+    g = n2v.graph.DeviceGraph.from_arcs(src, dst, None, n_vertices=1 << 20)
+    deg = g.degrees()
+    assert int(deg.max()) == 10000 and int((deg == 10000).sum()) >= 16
+    assert g.flags & 1 and g.flags & 4 and not (g.flags & 2)            # unit weights, simple, NOT symmetric
+    start = g.start_vertices()
+    walks, alive, stats = g.walk(start, 10, 80, 0.25, 4.0, seed=7, collect_stats=True)
+    assert g.ratio is not None and stats["fold_hits"] > 0                # general fold engaged
+    assert stats["steps"] == int(alive.sum()) * 80 + 0 * stats["dead"] or stats["dead"] > 0
+    keys = torch.sort((src.long() << 32) | dst.long()).values
+    sample = walks[alive][:: 64]
+    hop = ((sample[:, :-1].long() << 32) | sample[:, 1:].long()).reshape(-1)
+    pos = torch.searchsorted(keys, hop).clamp(max=keys.numel() - 1)
+    assert bool((keys[pos] == hop).all())                                # every sampled hop is an arc
+    assert torch.equal(walks[:, 0], start.repeat_interleave(10))
+    w2, a2, _ = g.walk(start[:1000], 10, 80, 0.25, 4.0, seed=7)
+    assert torch.equal(w2, walks[:10000]) and torch.equal(a2, alive[:10000])
+    rw, ra, rs = _replay(g, 0.25, 4.0, start[:40].cpu().numpy(), 10, 80, 7)
+    assert np.array_equal(rw[:, :81], walks[:400].cpu().numpy())
