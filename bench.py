@@ -67,6 +67,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(workload, kernel):
+    """DRAM bytes per launch measured by ncu for this workload/kernel (profiles/ncu_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(workload, {}).get(kernel)
+    except OSError:
+        return None
+
+
 def walk_bytes_per_step(stats):
     """16 B vertex record + T * (16 B arc record + 4 B * probes) + 4 B store.
     (The arc record is 16 B here, not the 12 B of the survey's sketch.)"""
@@ -235,7 +244,7 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------
-def bench_sgns(args, torch, dist, dev, world, rank, walks, w, flush, host_walks):
+def bench_sgns(args, torch, dist, dev, world, rank, walks, w, flush, host_walks, clocks=None):
     """Timed region: `steps` SGNS epochs (one kernel launch each; + the NCCL model-averaging
     allreduce when world > 1) over the walk matrix already in HBM.  e2e: host walk matrix in,
     Node2VecGensim.fit() (H2D + vocab + tables + init + 1 epoch), host embeddings out."""
@@ -261,6 +270,8 @@ def bench_sgns(args, torch, dist, dev, world, rank, walks, w, flush, host_walks)
         b.record()
         pairs += m.train_stats["pairs"]
     torch.cuda.synchronize()
+    if clocks is not None:
+        clocks.__exit__()
     if world > 1:
         dist.barrier()
     ms = [a.elapsed_time(b) for a, b in ev]
@@ -308,7 +319,9 @@ def bench_sgns(args, torch, dist, dev, world, rank, walks, w, flush, host_walks)
                 "h2d_bytes_per_step": int(host_walks.numel() * 4), "d2h_bytes_per_step": int(d2h),
                 "what": "Node2VecGensim(host walks).fit(): H2D + vocab_count + sgns_prepare + init + 1 epoch + D2H vectors"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "sgns_kernel", "bytes_per_pair": b_pair, "kernel_ms": kernel_ms,
+                     "traffic": ncu_traffic(args.workload, "sgns_kernel"), "kernel": "sgns_kernel",
+                     "bytes_per_pair": b_pair, "kernel_ms": kernel_ms,
+                     "algorithmic_bytes_per_launch": (pairs / args.steps) * b_pair,
                      "pairs_per_launch": pairs / args.steps, "peak_source": peak_src},
     }
 
@@ -421,13 +434,16 @@ def main():
     if world > 1:
         dist.barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clocks:
-        for a, b in ev:
-            flush.fill_(1)               # L2 flush between timed iterations (outside the events)
-            a.record()
-            one_pass()
-            b.record()
-        torch.cuda.synchronize()
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()                   # sampled through BOTH timed regions (walk, then SGNS)
+    for a, b in ev:
+        flush.fill_(1)                   # L2 flush between timed iterations (outside the events)
+        a.record()
+        one_pass()
+        b.record()
+    torch.cuda.synchronize()
+    if args.no_sgns:
+        clocks.__exit__()
     if world > 1:
         dist.barrier()
     ms = [a.elapsed_time(b) for a, b in ev]
@@ -471,7 +487,8 @@ def main():
     # ---- SGNS half: one epoch of skip-gram negative sampling over this rank's walk matrix
     sgns = None
     if not args.no_sgns:
-        sgns = bench_sgns(args, torch, dist, dev, world, rank, out[:, : w["walk_length"] + 1], w, flush, host_out)
+        sgns = bench_sgns(args, torch, dist, dev, world, rank, out[:, : w["walk_length"] + 1], w, flush, host_out,
+                          clocks)
 
     if rank != 0:
         if world > 1:
@@ -494,7 +511,9 @@ def main():
                 "d2h_bytes_per_step": int(host_out.numel() * 4),
                 "what": "fugue.random_walk(host arcs) = H2D + csr_build + alias_build + walk, then D2H of the walk matrix"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "walk_kernel", "bytes_per_step": b_step,
+                     "traffic": ncu_traffic(name, "walk_kernel"), "kernel": "walk_kernel", "bytes_per_step": b_step,
+                     "algorithmic_bytes_per_launch": steps_per_pass * b_step,
+                     "sectors_per_step": (stats["trials"] + stats["probes"]) / max(stats["steps"], 1),
                      "trials_per_step": T, "probes_per_trial": lp, "kernel_ms": kernel_ms, "peak_source": peak_src,
                      "note": "graph (10 MB) is L2-resident: effective-bandwidth figure, see profiles/"},
         "clocks": clocks.summary(),

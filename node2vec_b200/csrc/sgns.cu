@@ -62,13 +62,14 @@ struct Row {
   float4 v[NV];
 };
 
-template <int NV>
+// FULL: dim == NV * 128, every lane owns NV whole float4 (no tail predicate)
+template <int NV, bool FULL>
 __device__ __forceinline__ Row<NV> load_row(const float* __restrict__ base, int32_t dim, int lane) {
   Row<NV> r;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int d = (i * 32 + lane) * 4;
-    r.v[i] = d < dim ? *reinterpret_cast<const float4*>(base + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+    r.v[i] = (FULL || d < dim) ? *reinterpret_cast<const float4*>(base + d) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   return r;
 }
@@ -101,13 +102,13 @@ __device__ __forceinline__ void axpy(Row<NV>& acc, float g, const Row<NV>& x) {
 }
 
 // global row += g * x  (ATOMIC: vector reduction; else read-modify-write of the value we loaded)
-template <int NV, bool ATOMIC>
+template <int NV, bool ATOMIC, bool FULL>
 __device__ __forceinline__ void update_row(float* __restrict__ base, int32_t dim, int lane, float g,
                                            const Row<NV>& x, const Row<NV>& loaded) {
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int d = (i * 32 + lane) * 4;
-    if (d < dim) {
+    if (FULL || d < dim) {
       float4* p = reinterpret_cast<float4*>(base + d);
       if (ATOMIC) {
         atomicAdd(p, make_float4(g * x.v[i].x, g * x.v[i].y, g * x.v[i].z, g * x.v[i].w));
@@ -120,13 +121,13 @@ __device__ __forceinline__ void update_row(float* __restrict__ base, int32_t dim
 }
 
 // global row += delta
-template <int NV, bool ATOMIC>
+template <int NV, bool ATOMIC, bool FULL>
 __device__ __forceinline__ void add_row(float* __restrict__ base, int32_t dim, int lane, const Row<NV>& delta,
                                         const Row<NV>& loaded) {
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int d = (i * 32 + lane) * 4;
-    if (d < dim) {
+    if (FULL || d < dim) {
       float4* p = reinterpret_cast<float4*>(base + d);
       if (ATOMIC) {
         atomicAdd(p, delta.v[i]);
@@ -145,8 +146,17 @@ __device__ __forceinline__ float sigmoid_table(const float* table, float f) {
   return table[static_cast<int>((f + kMaxExp) * (kExpTable / kMaxExp / 2.0f))];
 }
 
-template <int NV, bool ATOMIC, bool TRACE>
-__global__ void __launch_bounds__(kBlock, N2V_SGNS_MIN_BLOCKS) sgns_kernel(const __grid_constant__ SgnsArgs A) {
+// g = (label - sigmoid(f)) * alpha, or 0 when the target is skipped / clipped (|f| >= 6).
+// Branch-free: the index is clamped into the table, the result is zeroed by `ok`.
+__device__ __forceinline__ float gradient(const float* table, float f, float label, float alpha, bool ok) {
+  const float fc = fminf(fmaxf(f, -kMaxExp), kMaxExp - 1e-3f);
+  const float g = (label - sigmoid_table(table, fc)) * alpha;
+  return ok ? g : 0.0f;
+}
+
+template <int NV, bool ATOMIC, bool TRACE, bool FULL>
+__global__ void __launch_bounds__(kBlock, NV == 1 ? N2V_SGNS_MIN_BLOCKS : (NV == 2 ? 2 : 1))
+sgns_kernel(const __grid_constant__ SgnsArgs A) {
   extern __shared__ int32_t smem[];
   __shared__ float exp_table[kExpTable];
   for (int i = threadIdx.x; i < kExpTable; i += kBlock) exp_table[i] = __ldg(A.exp_table + i);
@@ -157,7 +167,8 @@ __global__ void __launch_bounds__(kBlock, N2V_SGNS_MIN_BLOCKS) sgns_kernel(const
   constexpr bool tracing = TRACE;
   if (tracing && (blockIdx.x != 0 || wib != 0)) return;   // trace mode: ONE warp, walks in order
   const int64_t n_warps = tracing ? 1 : static_cast<int64_t>(gridDim.x) * kWarps;
-  unsigned long long c_pairs = 0, c_kept = 0, c_negskip = 0, c_clip = 0;
+  unsigned long long c_pairs = 0, c_kept = 0;
+  uint32_t c_negskip = 0, c_clip = 0;   // per-warp; far below 2^32 per launch share
   int64_t trace_pos = 0;
   const int K = A.negative;
   const double total_words = static_cast<double>(A.total_walks) * static_cast<double>(A.len);
@@ -212,12 +223,12 @@ __global__ void __launch_bounds__(kBlock, N2V_SGNS_MIN_BLOCKS) sgns_kernel(const
       if (j1 - j0 <= 1) continue;
       const int32_t wi = sent[i];
       float* pos_ptr = A.syn1neg + static_cast<int64_t>(wi) * A.dim;
-      Row<NV> pos = load_row<NV>(pos_ptr, A.dim, lane);   // stays in registers across the window
+      Row<NV> pos = load_row<NV, FULL>(pos_ptr, A.dim, lane);   // stays in registers across the window
       for (int j = j0; j < j1; ++j) {
         if (j == i) continue;
         const int32_t wj = sent[j];
         float* in_ptr = A.syn0 + static_cast<int64_t>(wj) * A.dim;
-        const Row<NV> in = load_row<NV>(in_ptr, A.dim, lane);
+        const Row<NV> in = load_row<NV, FULL>(in_ptr, A.dim, lane);
         Row<NV> work;
 #pragma unroll
         for (int q = 0; q < NV; ++q) work.v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -226,17 +237,16 @@ __global__ void __launch_bounds__(kBlock, N2V_SGNS_MIN_BLOCKS) sgns_kernel(const
           trow = A.trace + trace_pos * (2 + K);
           if (lane == 0) { trow[0] = wi; trow[1] = wj; A.trace_alpha[trace_pos] = alpha; }
         }
-        // positive target: the centre word
+        // positive target: the centre word (row in registers).  Branch-free: a clipped target
+        // (|f| >= 6, gensim skips it) gets g = 0 and its reduction adds zeros.
         {
           const float f = dot_rows<NV>(in, pos);
-          if (f > -kMaxExp && f < kMaxExp) {
-            const float g = (1.0f - sigmoid_table(exp_table, f)) * alpha;
-            axpy<NV>(work, g, pos);
-            update_row<NV, ATOMIC>(pos_ptr, A.dim, lane, g, in, pos);
-            axpy<NV>(pos, g, in);
-          } else {
-            ++c_clip;
-          }
+          const bool ok = f > -kMaxExp && f < kMaxExp;
+          const float g = gradient(exp_table, f, 1.0f, alpha, ok);
+          c_clip += ok ? 0u : 1u;
+          axpy<NV>(work, g, pos);
+          if (ATOMIC || ok) update_row<NV, ATOMIC, FULL>(pos_ptr, A.dim, lane, g, in, pos);
+          axpy<NV>(pos, g, in);
         }
         // K negatives ~ count^0.75, one 8-byte alias gather each
         for (int d = 0; d < K; ++d) {
@@ -245,24 +255,20 @@ __global__ void __launch_bounds__(kBlock, N2V_SGNS_MIN_BLOCKS) sgns_kernel(const
           const uint32_t slot = __umulhi(u1, A.n_vertices);
           const int2 e = __ldg(A.neg_table + slot);
           const int32_t tgt = (u2 < static_cast<uint32_t>(e.x)) ? static_cast<int32_t>(slot) : e.y;
-          if (tgt == wi) {
-            ++c_negskip;
-            if (TRACE && trow && lane == 0) trow[2 + d] = -1;
-            continue;
-          }
-          if (TRACE && trow && lane == 0) trow[2 + d] = tgt;
+          const bool skip = tgt == wi;                      // gensim: a negative equal to the centre is skipped
+          if (TRACE && trow && lane == 0) trow[2 + d] = skip ? -1 : tgt;
           float* t_ptr = A.syn1neg + static_cast<int64_t>(tgt) * A.dim;
-          const Row<NV> tr = load_row<NV>(t_ptr, A.dim, lane);
+          const Row<NV> tr = load_row<NV, FULL>(t_ptr, A.dim, lane);
           const float f = dot_rows<NV>(in, tr);
-          if (f > -kMaxExp && f < kMaxExp) {
-            const float g = (0.0f - sigmoid_table(exp_table, f)) * alpha;
-            axpy<NV>(work, g, tr);
-            update_row<NV, ATOMIC>(t_ptr, A.dim, lane, g, in, tr);
-          } else {
-            ++c_clip;
-          }
+          const bool in_range = f > -kMaxExp && f < kMaxExp;
+          const bool ok = in_range && !skip;
+          const float g = gradient(exp_table, f, 0.0f, alpha, ok);
+          c_negskip += skip ? 1u : 0u;
+          c_clip += (!skip && !in_range) ? 1u : 0u;
+          axpy<NV>(work, g, tr);
+          if (ATOMIC || ok) update_row<NV, ATOMIC, FULL>(t_ptr, A.dim, lane, g, in, tr);
         }
-        add_row<NV, ATOMIC>(in_ptr, A.dim, lane, work, in);
+        add_row<NV, ATOMIC, FULL>(in_ptr, A.dim, lane, work, in);
         ++c_pairs;
         if (TRACE) ++trace_pos;
       }
@@ -272,21 +278,33 @@ __global__ void __launch_bounds__(kBlock, N2V_SGNS_MIN_BLOCKS) sgns_kernel(const
   if (A.stats && lane == 0) {
     if (c_pairs) atomicAdd(A.stats + 0, c_pairs);
     if (c_kept) atomicAdd(A.stats + 1, c_kept);
-    if (c_negskip) atomicAdd(A.stats + 2, c_negskip);
-    if (c_clip) atomicAdd(A.stats + 3, c_clip);
+    if (c_negskip) atomicAdd(A.stats + 2, static_cast<unsigned long long>(c_negskip));
+    if (c_clip) atomicAdd(A.stats + 3, static_cast<unsigned long long>(c_clip));
   }
+}
+
+template <int NV, bool FULL>
+cudaError_t launch_full(const SgnsArgs& A, bool atomic, int grid, size_t smem, cudaStream_t stream) {
+#define N2V_SGNS_GO(AT, TR)                                                                              \
+  do {                                                                                                   \
+    if (smem > 48 * 1024)                                                                                \
+      cudaFuncSetAttribute(sgns_kernel<NV, AT, TR, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                           static_cast<int>(smem));                                                      \
+    sgns_kernel<NV, AT, TR, FULL><<<grid, kBlock, smem, stream>>>(A);                                   \
+  } while (0)
+  if (A.trace) {
+    if (atomic) N2V_SGNS_GO(true, true); else N2V_SGNS_GO(false, true);
+  } else {
+    if (atomic) N2V_SGNS_GO(true, false); else N2V_SGNS_GO(false, false);
+  }
+#undef N2V_SGNS_GO
+  return cudaGetLastError();
 }
 
 template <int NV>
 cudaError_t launch(const SgnsArgs& A, bool atomic, int grid, size_t smem, cudaStream_t stream) {
-  if (A.trace) {
-    if (atomic) sgns_kernel<NV, true, true><<<grid, kBlock, smem, stream>>>(A);
-    else sgns_kernel<NV, false, true><<<grid, kBlock, smem, stream>>>(A);
-  } else {
-    if (atomic) sgns_kernel<NV, true, false><<<grid, kBlock, smem, stream>>>(A);
-    else sgns_kernel<NV, false, false><<<grid, kBlock, smem, stream>>>(A);
-  }
-  return cudaGetLastError();
+  return A.dim == NV * 128 ? launch_full<NV, true>(A, atomic, grid, smem, stream)
+                           : launch_full<NV, false>(A, atomic, grid, smem, stream);
 }
 
 }  // namespace
@@ -354,16 +372,7 @@ extern "C" int n2v_sgns_train(const int32_t* walks, int64_t n_walks, int32_t len
   const int nv = (P->dim + 127) / 128;
   cudaError_t err;
   const bool atomic = P->atomic_updates != 0;
-#define N2V_SGNS_LAUNCH(NVV)                                                                           \
-  do {                                                                                                 \
-    if (smem > 48 * 1024) {                                                                            \
-      cudaFuncSetAttribute(sgns_kernel<NVV, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-      cudaFuncSetAttribute(sgns_kernel<NVV, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      cudaFuncSetAttribute(sgns_kernel<NVV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-      cudaFuncSetAttribute(sgns_kernel<NVV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-    }                                                                                                  \
-    err = launch<NVV>(A, atomic, grid, smem, stream);                                                  \
-  } while (0)
+#define N2V_SGNS_LAUNCH(NVV) err = launch<NVV>(A, atomic, grid, smem, stream)
   if (nv <= 1) N2V_SGNS_LAUNCH(1);
   else if (nv <= 2) N2V_SGNS_LAUNCH(2);
   else if (nv <= 4) N2V_SGNS_LAUNCH(4);
