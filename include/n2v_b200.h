@@ -307,8 +307,8 @@ typedef struct n2v_sgns_params {
 /* K3: one epoch of skip-gram negative sampling over walks[n_walks][pitch] (`len` tokens each).
  * One warp per walk: sub-sample, then for every centre i draw the reduced window and for every
  * context j update (syn0[walk[j]], syn1neg[walk[i]], syn1neg[K negatives]).
- * stats (device, 4 x uint64, accumulated): [0] pairs trained, [1] tokens kept, [2] negatives
- * skipped (== centre), [3] targets skipped by the |f| >= 6 clip.
+ * stats (device, 4 x uint64, accumulated): [0] pairs trained, [1] tokens kept; and, counted only
+ * in trace mode (diagnostics), [2] negatives skipped (== centre), [3] targets clipped (|f| >= 6).
  * trace (device int32[trace_cap][2 + negative], may be NULL): when given, ONE warp runs the
  * walks in order and records every pair {centre, context, negatives (-1 = skipped)} and its
  * alpha in trace_alpha; pairs beyond trace_cap are trained but not recorded. */

@@ -27,6 +27,9 @@ constexpr int kWarps = kBlock / 32;
 #ifndef N2V_SGNS_MIN_BLOCKS
 #define N2V_SGNS_MIN_BLOCKS 4  // measured: 4 blocks (64 regs) beats 1/3 (fewer warps) and 5/6 (spills)
 #endif
+#ifndef N2V_SGNS_MIN_BLOCKS_NV2
+#define N2V_SGNS_MIN_BLOCKS_NV2 3
+#endif
 constexpr float kMaxExp = 6.0f;
 
 struct SgnsArgs {
@@ -155,7 +158,7 @@ __device__ __forceinline__ float gradient(const float* table, float f, float lab
 }
 
 template <int NV, bool ATOMIC, bool TRACE, bool FULL>
-__global__ void __launch_bounds__(kBlock, NV == 1 ? N2V_SGNS_MIN_BLOCKS : (NV == 2 ? 2 : 1))
+__global__ void __launch_bounds__(kBlock, NV == 1 ? N2V_SGNS_MIN_BLOCKS : (NV == 2 ? N2V_SGNS_MIN_BLOCKS_NV2 : 1))
 sgns_kernel(const __grid_constant__ SgnsArgs A) {
   extern __shared__ int32_t smem[];
   __shared__ float exp_table[kExpTable];
@@ -243,7 +246,7 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
           const float f = dot_rows<NV>(in, pos);
           const bool ok = f > -kMaxExp && f < kMaxExp;
           const float g = gradient(exp_table, f, 1.0f, alpha, ok);
-          c_clip += ok ? 0u : 1u;
+          if (TRACE) c_clip += ok ? 0u : 1u;
           axpy<NV>(work, g, pos);
           if (ATOMIC || ok) update_row<NV, ATOMIC, FULL>(pos_ptr, A.dim, lane, g, in, pos);
           axpy<NV>(pos, g, in);
@@ -263,8 +266,10 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
           const bool in_range = f > -kMaxExp && f < kMaxExp;
           const bool ok = in_range && !skip;
           const float g = gradient(exp_table, f, 0.0f, alpha, ok);
-          c_negskip += skip ? 1u : 0u;
-          c_clip += (!skip && !in_range) ? 1u : 0u;
+          if (TRACE) {   // diagnostics only in the single-warp trace build
+            c_negskip += skip ? 1u : 0u;
+            c_clip += (!skip && !in_range) ? 1u : 0u;
+          }
           axpy<NV>(work, g, tr);
           if (ATOMIC || ok) update_row<NV, ATOMIC, FULL>(t_ptr, A.dim, lane, g, in, tr);
         }
