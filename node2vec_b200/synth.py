@@ -98,6 +98,31 @@ def rmat_device(scale: int, edge_factor: int = 16, seed: int = 42, device=None,
     return torch.cat([lo, hi]).to(torch.int32), torch.cat([hi, lo]).to(torch.int32)
 
 
+def products_like_device(n: int = 2449029, n_edges: int = 61859140, seed: int = 42, device=None):
+    """BASELINE configs[3]: an ogbn-products-shaped graph (2.4 M vertices, ~62 M undirected edges):
+    R-MAT scale 22 folded onto n vertices.  Returns symmetrised int32 CUDA tensors."""
+    import torch
+    device = torch.device(device if device is not None else "cuda")
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    a, b, c = 0.57, 0.19, 0.19
+    m = int(n_edges * 1.08)                      # head-room for the duplicates removed below
+    src = torch.zeros(m, dtype=torch.int64, device=device)
+    dst = torch.zeros(m, dtype=torch.int64, device=device)
+    for _ in range(22):
+        r = torch.rand(m, device=device, generator=gen)
+        src = (src << 1) | (r >= a + b).long()
+        dst = (dst << 1) | (((r >= a) & (r < a + b)) | (r >= a + b + c)).long()
+    perm = torch.randperm(1 << 22, device=device, generator=gen)
+    src, dst = perm[src] % n, perm[dst] % n
+    lo, hi = torch.minimum(src, dst), torch.maximum(src, dst)
+    keys = torch.unique(((lo << 32) | hi)[lo != hi])
+    if keys.numel() > n_edges:
+        keys = keys[torch.randperm(keys.numel(), device=device, generator=gen)[:n_edges]]
+    lo, hi = keys >> 32, keys & 0xFFFFFFFF
+    return torch.cat([lo, hi]).to(torch.int32), torch.cat([hi, lo]).to(torch.int32)
+
+
 def rmat_host(scale: int, edge_factor: int = 16, seed: int = 42, abcd=(0.57, 0.19, 0.19, 0.05)):
     """numpy twin of rmat_device for boxes without a GPU (CPU baseline legs)."""
     rng = np.random.default_rng(seed)

@@ -570,3 +570,35 @@ def test_full_size_properties_config3(n2v):
     assert torch.equal(w2, walks[:10000]) and torch.equal(a2, alive[:10000])
     rw, ra, rs = _replay(g, 0.25, 4.0, start[:40].cpu().numpy(), 10, 80, 7)
     assert np.array_equal(rw[:, :81], walks[:400].cpu().numpy())
+
+
+def test_full_size_properties_config4(n2v):
+    """BASELINE configs[3] shape: 2.4 M vertices / ~62 M edges (124 M arcs, a 6.5 GB packed graph),
+    walk length 80; 2 walks per vertex here (the bench shape is 10) to keep the test short."""
+    torch = n2v.torch
+    from node2vec_b200 import synth
+    src, dst = synth.products_like_device(seed=42)
+    V = 2449029
+    assert 120_000_000 < src.numel() < 124_000_000
+    g = n2v.graph.DeviceGraph.from_arcs(src, dst, None, n_vertices=V)
+    assert g.flags & 7 == 7 and g.nbytes() > 6e9
+    start = g.start_vertices()
+    walks, alive, stats = g.walk(start, 2, 80, 0.5, 2.0, seed=3, collect_stats=True)
+    assert bool(alive.all()) and stats["steps"] == walks.shape[0] * 80 and stats["fallbacks"] == 0
+    keys = torch.sort((src.long() << 32) | dst.long()).values
+    del src, dst
+    sample = walks[:: 97]
+    hop = ((sample[:, :-1].long() << 32) | sample[:, 1:].long()).reshape(-1)
+    pos = torch.searchsorted(keys, hop).clamp(max=keys.numel() - 1)
+    assert bool((keys[pos] == hop).all())
+    del keys, hop, pos
+    w2, _, _ = g.walk(start[50000:50500], 2, 80, 0.5, 2.0, seed=3)
+    assert torch.equal(w2, walks[100000:101000])
+    rw, ra, rs = _replay(g, 0.5, 2.0, start[:100].cpu().numpy(), 2, 80, 3)
+    assert np.array_equal(rw[:, :81], walks[:200].cpu().numpy())
+    # SGNS at the config's width (D = 256) on a slice of these walks: trains and stays finite
+    from node2vec_b200.sgns import Word2Vec
+    m = Word2Vec(size=256, sg=1, negative=5, min_count=1, iter=1, seed=2)
+    m.build_vocab(walks[:200000])
+    m.train(walks[:200000])
+    assert m.train_stats["pairs"] > 200000 * 81 * 4 and bool(torch.isfinite(m.syn0).all())
