@@ -89,7 +89,7 @@ class Node2VecGensim(Node2VecBase):
         if dev is not None:
             return dev
         walks = self.walks["walk"] if not hasattr(self.walks, "as_pandas") else self.walks.as_pandas()["walk"]
-        return np.array(walks.tolist())
+        return np.asarray(walks.tolist())
 
     def fit(self) -> Word2Vec:
         self.model = Word2Vec(sentences=self._sentences(), **self.w2v_params)

@@ -47,7 +47,18 @@ class KeyedVectors(object):
         self._vocab: Optional[Dict[str, Vocab]] = {}
         self._index2word: Optional[list] = []
         self._lazy = None       # (ids in first-appearance order, rank by count, counts, keep thresholds)
-        self.vectors = np.zeros((0, vector_size), dtype=np.float32)
+        self._vectors = np.zeros((0, vector_size), dtype=np.float32)
+        self._vectors_fn = None  # device -> host copy of the table, run on first access after training
+
+    @property
+    def vectors(self) -> np.ndarray:
+        if self._vectors_fn is not None:
+            self._vectors, self._vectors_fn = self._vectors_fn(), None
+        return self._vectors
+
+    @vectors.setter
+    def vectors(self, value):
+        self._vectors, self._vectors_fn = value, None
 
     # The dict of Vocab objects costs ~1 us per vertex to build in Python; it is materialised on
     # first access only (training never needs it).
@@ -254,11 +265,13 @@ class Word2Vec(object):
         n2v_dist.average_tables((self.syn0, self.syn1neg), self.process_group, scale)
 
     def _sync_vectors(self) -> None:
-        self.wv.vectors = self.syn0[self._row_of_index].cpu().numpy()
+        # lazy: the [vocab, size] host copy is made when somebody reads wv.vectors / wv[token]
+        self.wv._vectors_fn = lambda: self.syn0[self._row_of_index].cpu().numpy()
 
     # ------------------------------------------------------------------ persistence
     def save(self, fname: str) -> None:
         self.wv._materialise()
+        _ = self.wv.vectors
         state = {k: v for k, v in self.__dict__.items()
                  if k not in ("syn0", "syn1neg", "_keep", "_neg", "_exp", "_row_of_index", "process_group")}
         state["syn0"] = None if self.syn0 is None else self.syn0.cpu().numpy()
