@@ -243,10 +243,15 @@ int n2v_ratio_build(const n2v_graph_t* graph, float* ratio_out, void* stream);
 
 
 /* ---- peer-shareable device buffers (vertex-partitioned CSR over NVLink) ----------------
- * The one place the library allocates: CUDA IPC needs whole cudaMalloc allocations.  A rank
- * allocates its part's arcs / hash / col / weight with n2v_ipc_alloc, exports a 64-byte handle
- * per buffer, peers open it (peer access is enabled lazily by the driver) and put the mapped
- * address into n2v_graph_t.parts[owner].  All pointers are plain device addresses. */
+ * The one place the library allocates.  A rank allocates its part's arcs / hash / col / weight
+ * with n2v_ipc_alloc (CUDA virtual-memory-management allocation, 2 MiB pages, mapped read/write
+ * on the current device), exports a 64-byte handle per buffer
+ *     { int32 fd, int32 owner device, uint64 mapped size, zeros }
+ * whose POSIX file descriptor the HOST transfers to the peer processes (SCM_RIGHTS); a peer
+ * rewrites the fd field with its own copy and calls n2v_ipc_open, which maps the allocation
+ * with its native page size on the caller's current device (NVLink peer loads), and puts the
+ * address into n2v_graph_t.parts[owner].  (cudaIpc* mappings were measured ~50x slower for
+ * random gathers beyond ~1 GB of remote footprint.) */
 #define N2V_IPC_HANDLE_BYTES 64
 int n2v_ipc_alloc(size_t bytes, void** ptr_host);
 int n2v_ipc_free(void* ptr);

@@ -62,38 +62,3 @@ extern "C" int n2v_walk_consts(double return_param, double inout_param, uint32_t
   out->max_trials = 256;
   return N2V_OK;
 }
-
-// ---- peer-shareable buffers (CUDA IPC) -----------------------------------------------------
-extern "C" int n2v_ipc_alloc(size_t bytes, void** ptr) {
-  N2V_CHECK_ARG(ptr != nullptr, "n2v_ipc_alloc: NULL out pointer");
-  *ptr = nullptr;
-  N2V_CUDA(cudaMalloc(ptr, bytes ? bytes : 256));
-  return N2V_OK;
-}
-
-extern "C" int n2v_ipc_free(void* ptr) {
-  if (ptr) N2V_CUDA(cudaFree(ptr));
-  return N2V_OK;
-}
-
-extern "C" int n2v_ipc_export(const void* ptr, unsigned char* handle) {
-  N2V_CHECK_ARG(ptr && handle, "n2v_ipc_export: NULL argument");
-  static_assert(sizeof(cudaIpcMemHandle_t) == N2V_IPC_HANDLE_BYTES, "IPC handle size");
-  cudaIpcMemHandle_t h;
-  N2V_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)));
-  memcpy(handle, &h, sizeof(h));
-  return N2V_OK;
-}
-
-extern "C" int n2v_ipc_open(const unsigned char* handle, void** ptr) {
-  N2V_CHECK_ARG(ptr && handle, "n2v_ipc_open: NULL argument");
-  cudaIpcMemHandle_t h;
-  memcpy(&h, handle, sizeof(h));
-  N2V_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
-  return N2V_OK;
-}
-
-extern "C" int n2v_ipc_close(void* ptr) {
-  if (ptr) N2V_CUDA(cudaIpcCloseMemHandle(ptr));
-  return N2V_OK;
-}

@@ -234,6 +234,44 @@ def _ipc_tensor(lib, shape, dtype: torch.dtype, device) -> Tuple[torch.Tensor, i
     return torch.as_tensor(_RawBuffer(ptr.value, shape, typestr), device=device), int(ptr.value)
 
 
+def _exchange_fds(my_fds, rank: int, world: int, group) -> Dict[int, list]:
+    """Give every peer process its own copy of this rank's shareable-handle file descriptors
+    (SCM_RIGHTS over Unix sockets) and collect theirs.  Returns {peer rank: [fds]}."""
+    import socket
+    import tempfile
+    import threading
+    import torch.distributed as dist
+    path = os.path.join(tempfile.gettempdir(), f"n2v_ipc_{os.getpid()}_{rank}.sock")
+    if os.path.exists(path):
+        os.unlink(path)
+    server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    server.bind(path)
+    server.listen(world)
+    paths = [None] * world
+    dist.all_gather_object(paths, path, group=group)
+
+    def serve():
+        for _ in range(world - 1):
+            conn, _ = server.accept()
+            socket.send_fds(conn, [b"n2v"], list(my_fds))
+            conn.close()
+    t = threading.Thread(target=serve, daemon=True)
+    t.start()
+    got = {}
+    for p in range(world):
+        if p == rank:
+            continue
+        c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        c.connect(paths[p])
+        _, fds, _, _ = socket.recv_fds(c, 16, len(my_fds))
+        c.close()
+        got[p] = list(fds)
+    t.join()
+    server.close()
+    os.unlink(path)
+    return got
+
+
 class PartitionedGraph(DeviceGraph):
     """One rank's part of a vertex-range-partitioned graph (BASELINE configs[4]).
 
@@ -309,16 +347,20 @@ class PartitionedGraph(DeviceGraph):
             if assume_symmetric and (g.flags & _lib.GRAPH_SIMPLE):
                 g.flags |= _lib.GRAPH_SYMMETRIC
             g.n_vertices, g.n_arcs, g.n_local_arcs = int(n_vertices), int(totals.item()), A
-            # exchange IPC handles and map the peers' parts
-            handles = []
-            for t in (g.arcs, g.col, g.weight, g.hash):
+            # export shareable handles, hand the peers their own copies of the fds, map their parts
+            import struct
+            handles, my_fds = [], []
+            own = {"arcs": g._ipc_ptrs[3], "col": g._ipc_ptrs[0], "weight": g._ipc_ptrs[1], "hash": g._ipc_ptrs[2]}
+            for name in ("arcs", "col", "weight", "hash"):
                 buf = C.create_string_buffer(64)
-                ptr = [q for q in g._ipc_ptrs if q == t.data_ptr()] or [t.data_ptr()]
-                _lib.check(lib.n2v_ipc_export(C.c_void_p(ptr[0]), buf), "n2v_ipc_export")
+                _lib.check(lib.n2v_ipc_export(C.c_void_p(own[name]), buf), "n2v_ipc_export")
                 handles.append(bytes(buf.raw))
+                my_fds.append(struct.unpack_from("<i", buf.raw, 0)[0])
             all_handles = [None] * G
+            peer_fds = {}
             if G > 1:
                 dist.all_gather_object(all_handles, handles, group=group)
+                peer_fds = _exchange_fds(my_fds, rank, G, group)
             else:
                 all_handles[0] = handles
             st = _lib.Graph()
@@ -331,14 +373,18 @@ class PartitionedGraph(DeviceGraph):
                     ptrs = [g.arcs.data_ptr(), g.col.data_ptr(), g.weight.data_ptr(), g.hash.data_ptr()]
                 else:
                     ptrs = []
-                    for h in all_handles[p_idx]:
+                    for h, fd in zip(all_handles[p_idx], peer_fds[p_idx]):
+                        local_h = struct.pack("<i", fd) + h[4:]          # the fd as it is known in THIS process
                         out = C.c_void_p()
-                        _lib.check(lib.n2v_ipc_open(h, C.byref(out)), "n2v_ipc_open")
+                        _lib.check(lib.n2v_ipc_open(local_h, C.byref(out)), "n2v_ipc_open")
+                        os.close(fd)
                         ptrs.append(int(out.value))
                         g._peer_ptrs.append(int(out.value))
                 st.parts[p_idx].arcs, st.parts[p_idx].col = ptrs[0], ptrs[1]
                 st.parts[p_idx].weight, st.parts[p_idx].hash = ptrs[2], ptrs[3]
             g._struct = st
+            for fd in my_fds:
+                os.close(fd)
             if G > 1:
                 dist.barrier(group=group)
         return g
