@@ -76,6 +76,24 @@ def ncu_traffic(workload, kernel):
         return None
 
 
+# measured on B200 with scripts/gather_peak.cu (profiles/r01_gather_peak.txt): random 32-byte
+# LDG.256 gathers, G sectors/s
+GATHER_CEILING = {"l2": 235.0, "hbm": 40.0}
+
+
+def gather_view(stats, steps, kernel_ms, graph_bytes):
+    """The walk as what it is -- a stream of random 32-byte sector gathers (one arc record per
+    trial, one hash bucket per membership test): achieved G sectors/s against the measured
+    random-gather ceiling of the level the graph lives in (L2 if it fits, else HBM)."""
+    sectors = (stats["trials"] + stats["probes"]) / max(stats["steps"], 1) * steps
+    achieved = sectors / (kernel_ms * 1e-3) / 1e9
+    level = "l2" if graph_bytes < 100e6 else "hbm"
+    return {"achieved_gsectors_per_s": achieved, "ceiling_gsectors_per_s": GATHER_CEILING[level], "level": level,
+            "frac": achieved / GATHER_CEILING[level],
+            "bytes_per_step_layout": 32.0 * (stats["trials"] + stats["probes"]) / max(stats["steps"], 1) + 4.0,
+            "note": "ceiling = scripts/gather_peak.cu on this GPU type; hub sectors that hit L2 let a DRAM-sized graph exceed the HBM figure slightly"}
+
+
 def walk_bytes_per_step(stats):
     """16 B vertex record + T * (16 B arc record + 4 B * probes) + 4 B store.
     (The arc record is 16 B here, not the 12 B of the survey's sketch.)"""
@@ -514,6 +532,7 @@ def main():
                      "traffic": ncu_traffic(name, "walk_kernel"), "kernel": "walk_kernel", "bytes_per_step": b_step,
                      "algorithmic_bytes_per_launch": steps_per_pass * b_step,
                      "sectors_per_step": (stats["trials"] + stats["probes"]) / max(stats["steps"], 1),
+                     "gather": gather_view(stats, steps_per_pass, kernel_ms, g.nbytes()),
                      "trials_per_step": T, "probes_per_trial": lp, "kernel_ms": kernel_ms, "peak_source": peak_src,
                      "note": "graph (10 MB) is L2-resident: effective-bandwidth figure, see profiles/"},
         "clocks": clocks.summary(),

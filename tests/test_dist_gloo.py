@@ -49,6 +49,38 @@ def _worker(rank, world_size, port, out_dir):
         dist.destroy_process_group()
 
 
+def _fd_worker(rank, world_size, port, out_dir):
+    """The SCM_RIGHTS hand-over used for the peer-shareable buffer handles: every rank ends up with
+    its OWN copies of every other rank's file descriptors."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        from node2vec_b200.graph import _exchange_fds
+        fds = []
+        for k in range(3):
+            path = os.path.join(out_dir, f"r{rank}_f{k}.txt")
+            with open(path, "w") as f:
+                f.write(f"rank {rank} file {k}")
+            fds.append(os.open(path, os.O_RDONLY))
+        got = _exchange_fds(fds, rank, world_size, None)
+        assert sorted(got) == [p for p in range(world_size) if p != rank]
+        for p, peer_fds in got.items():
+            assert len(peer_fds) == 3 and all(fd not in fds for fd in peer_fds)
+            for k, fd in enumerate(peer_fds):
+                assert os.pread(fd, 100, 0).decode() == f"rank {p} file {k}"   # shared open-file description: no seek
+                os.close(fd)
+        for fd in fds:
+            os.close(fd)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fd_exchange_three_ranks(tmp_path):
+    mp.spawn(_fd_worker, args=(3, _free_port(), str(tmp_path)), nprocs=3, join=True)
+
+
 def test_two_rank_bookkeeping(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
