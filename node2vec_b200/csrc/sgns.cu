@@ -45,6 +45,7 @@ struct SgnsArgs {
   int64_t trace_cap;
   int64_t n_walks, pitch, walk_offset, total_walks;
   uint32_t n_vertices;
+  uint32_t n_top;   // entries of the top-level negative table (0 = single level)
   int32_t len, len_cap, dim, window, negative, epochs, epoch, batch_words;
   float alpha, min_alpha;
   uint32_t key0, key1;
@@ -253,9 +254,17 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
         }
         // K negatives ~ count^0.75, one 8-byte alias gather each
         for (int d = 0; d < K; ++d) {
+          uint32_t lo = 0, span = A.n_vertices;
+          if (A.n_top) {   // two-level table: chunk ~ mass first (top level is L2-resident)
+            const uint32_t c0 = __umulhi(pcg_next(rnd), A.n_top);
+            const int2 te = __ldg(A.neg_table + A.n_vertices + c0);
+            const uint32_t c = (pcg_next(rnd) < static_cast<uint32_t>(te.x)) ? c0 : static_cast<uint32_t>(te.y);
+            lo = c * N2V_NEG_CHUNK;
+            span = min(static_cast<uint32_t>(N2V_NEG_CHUNK), A.n_vertices - lo);
+          }
           const uint32_t u1 = pcg_next(rnd);
           const uint32_t u2 = pcg_next(rnd);
-          const uint32_t slot = __umulhi(u1, A.n_vertices);
+          const uint32_t slot = lo + __umulhi(u1, span);
           const int2 e = __ldg(A.neg_table + slot);
           const int32_t tgt = (u2 < static_cast<uint32_t>(e.x)) ? static_cast<int32_t>(slot) : e.y;
           const bool skip = tgt == wi;                      // gensim: a negative equal to the centre is skipped
@@ -352,6 +361,7 @@ extern "C" int n2v_sgns_train(const int32_t* walks, int64_t n_walks, int32_t len
   A.walk_offset = P->walk_offset;
   A.total_walks = P->total_walks > 0 ? P->total_walks : n_walks;
   A.n_vertices = static_cast<uint32_t>(n_vertices);
+  A.n_top = static_cast<uint32_t>(n2v_neg_top_entries(n_vertices));
   A.len = len;
   A.len_cap = (len + 31) & ~31;
   A.dim = P->dim;

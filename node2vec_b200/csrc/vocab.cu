@@ -69,25 +69,157 @@ __global__ void thresholds(const int64_t* __restrict__ counts, int64_t n, int64_
   }
 }
 
-// one alias table over all ids (sequential Vose, same core as the per-vertex tables)
-__global__ void neg_table_kernel(double* __restrict__ probs, int64_t n, int32_t* __restrict__ work,
-                                 int32_t* __restrict__ table, int* __restrict__ ok) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// ---- negative-sampling alias table over all ids ----------------------------------------------
+// Not a reference-parity object (gensim bisects a cumulative table; any exact alias table of
+// count^0.75 gives the same law), so it is built for speed: ids are split into "small"
+// (scaled prob < 1) and "large" lists in parallel, their probabilities are packed next to them,
+// and ONE thread runs Vose's two-queue merge over the two packed streams.  The merge is
+// sequential but its loads are contiguous and independent of the arithmetic (a few ns per id,
+// ~1 s for 67 M ids) instead of a dependent global-memory round trip per id.
+__global__ void scale_and_split(const double* __restrict__ weight, int64_t n, const double* __restrict__ total,
+                                int32_t* __restrict__ ids, double* __restrict__ packed,
+                                unsigned long long* __restrict__ counters /* [0] smalls, [1] larges */) {
+  const double scale = static_cast<double>(n) / *total;
+  for (int64_t v = blockIdx.x * int64_t(kBlock) + threadIdx.x; v < n; v += int64_t(gridDim.x) * kBlock) {
+    const double p = weight[v] * scale;
+    const bool small = p < 1.0;
+    // warp-aggregated append: smalls grow from the front, larges from the back
+    const unsigned int active = __activemask();
+    const unsigned int m_small = __ballot_sync(active, small);
+    const unsigned int mine = small ? m_small : (active & ~m_small);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mine) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(counters + (small ? 0 : 1), static_cast<unsigned long long>(__popc(mine)));
+    base = __shfl_sync(active, base, leader);
+    const unsigned long long pos = base + __popc(mine & ((1u << lane) - 1u));
+    const int64_t slot = small ? static_cast<int64_t>(pos) : n - 1 - static_cast<int64_t>(pos);
+    ids[slot] = static_cast<int32_t>(v);
+    packed[slot] = p;
+  }
+}
+
+__device__ __forceinline__ uint32_t neg_thr(double p) {
+  if (p >= 1.0) return 0xFFFFFFFFu;
+  const double s = ceil(p * 4294967296.0);
+  return s >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(s);
+}
+
+// One warp: lanes stream the two packed lists through shared-memory windows (coalesced 1 KiB
+// refills), lane 0 runs the inherently sequential two-queue merge out of shared memory.
+constexpr int kWin = 1024;   // entries per window
+__global__ void __launch_bounds__(32) vose_merge(const int32_t* __restrict__ ids, const double* __restrict__ packed,
+                                                 int64_t n, const unsigned long long* __restrict__ counters,
+                                                 int32_t* __restrict__ table) {
+  __shared__ int32_t s_id[kWin], l_id[kWin];
+  __shared__ double s_p[kWin], l_p[kWin];
+  __shared__ int64_t sh_i, sh_j;
+  __shared__ int sh_carry, sh_carry_id, sh_done;
+  __shared__ double sh_carry_p;
+  if (blockIdx.x != 0) return;
+  const int lane = threadIdx.x;
   int2* out = reinterpret_cast<int2*>(table);
-  const bool good = n2v::build_alias_one(probs, static_cast<uint32_t>(n), N2V_SUM_NAIVE, work,
-                                         [&](uint32_t i, int32_t a) { out[i].y = a; });
-  *ok = good ? 1 : 0;
-  if (!good) return;
-  for (int64_t i = 0; i < n; ++i) {
-    const double p = probs[i];
-    uint32_t thr = 0xFFFFFFFFu;
-    if (p < 1.0) {
-      const double s = ceil(p * 4294967296.0);
-      thr = s >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(s);
-    } else {
-      out[i].y = static_cast<int32_t>(i);
+  const int64_t ns = static_cast<int64_t>(counters[0]), nl = static_cast<int64_t>(counters[1]);
+  if (lane == 0) { sh_i = 0; sh_j = 0; sh_carry = 0; sh_carry_id = 0; sh_carry_p = 0.0; sh_done = 0; }
+  __syncwarp();
+  int64_t s_base = 0, l_base = 0;       // list positions of the windows' first entries
+  int64_t s_have = 0, l_have = 0;       // entries valid in each window
+  for (;;) {
+    // refill whichever window lane 0 exhausted (both on the first pass)
+    const int64_t i = sh_i, j = sh_j;
+    if (i >= s_base + s_have && i < ns) {
+      s_base = i;
+      s_have = (ns - i) < kWin ? (ns - i) : kWin;
+      for (int k = lane; k < s_have; k += 32) { s_id[k] = ids[i + k]; s_p[k] = packed[i + k]; }
     }
-    out[i].x = static_cast<int32_t>(thr);
+    if (j >= l_base + l_have && j < nl) {
+      l_base = j;
+      l_have = (nl - j) < kWin ? (nl - j) : kWin;
+      for (int k = lane; k < l_have; k += 32) { l_id[k] = ids[n - 1 - (j + k)]; l_p[k] = packed[n - 1 - (j + k)]; }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      int64_t ii = sh_i, jj = sh_j;
+      bool carry = sh_carry != 0;
+      int32_t carry_id = sh_carry_id;
+      double carry_p = sh_carry_p;
+      // big_p lives in the window (updated in place) so a refill never loses it
+      while (jj < nl && jj < l_base + l_have && (carry || (ii < ns && ii < s_base + s_have))) {
+        int32_t sid;
+        double sp;
+        if (carry) { sid = carry_id; sp = carry_p; carry = false; }
+        else { sid = s_id[ii - s_base]; sp = s_p[ii - s_base]; ++ii; }
+        const int lk = static_cast<int>(jj - l_base);
+        const int32_t big_id = l_id[lk];
+        out[sid] = make_int2(static_cast<int32_t>(neg_thr(sp)), big_id);
+        const double bp = (l_p[lk] + sp) - 1.0;
+        l_p[lk] = bp;
+        if (bp < 1.0) { carry = true; carry_id = big_id; carry_p = bp; ++jj; }
+      }
+      sh_i = ii; sh_j = jj; sh_carry = carry ? 1 : 0; sh_carry_id = carry_id; sh_carry_p = carry_p;
+      // finished when the larges are exhausted, or no small is left to place
+      sh_done = (jj >= nl || (!carry && ii >= ns)) ? 1 : 0;
+    }
+    __syncwarp();
+    if (sh_done) break;
+  }
+  // leftovers (fp residue): they keep themselves with probability 1
+  const int64_t ii = sh_i, jj = sh_j;
+  if (lane == 0 && sh_carry) out[sh_carry_id] = make_int2(static_cast<int32_t>(0xFFFFFFFFu), sh_carry_id);
+  for (int64_t k = ii + lane; k < ns; k += 32) out[ids[k]] = make_int2(static_cast<int32_t>(0xFFFFFFFFu), ids[k]);
+  for (int64_t k = jj + lane; k < nl; k += 32) {
+    const int32_t id = ids[n - 1 - k];
+    out[id] = make_int2(static_cast<int32_t>(0xFFFFFFFFu), id);
+  }
+}
+
+// ---- two-level table for large id spaces: one thread per 1024-id chunk --------------------------
+// chunk alias table (global ids as aliases) + the chunk's mass; same Vose core as the per-vertex
+// graph tables (alias_core.cuh), probs / work list in the caller's scratch
+__global__ void chunk_tables(double* __restrict__ probs, int64_t n, int32_t* __restrict__ work,
+                             int32_t* __restrict__ table, double* __restrict__ chunk_mass) {
+  const int64_t n_chunks = (n + N2V_NEG_CHUNK - 1) / N2V_NEG_CHUNK;
+  int2* out = reinterpret_cast<int2*>(table);
+  for (int64_t c = blockIdx.x * int64_t(kBlock) + threadIdx.x; c < n_chunks; c += int64_t(gridDim.x) * kBlock) {
+    const int64_t lo = c * N2V_NEG_CHUNK;
+    const uint32_t m = static_cast<uint32_t>((n - lo) < N2V_NEG_CHUNK ? (n - lo) : N2V_NEG_CHUNK);
+    double* pr = probs + lo;
+    double mass = 0.0;
+    for (uint32_t i = 0; i < m; ++i) mass += pr[i];
+    chunk_mass[c] = mass;
+    if (!(mass > 0.0)) {   // a chunk of dropped ids: never selected by the top level
+      for (uint32_t i = 0; i < m; ++i) out[lo + i] = make_int2(static_cast<int32_t>(0xFFFFFFFFu), static_cast<int32_t>(lo + i));
+      continue;
+    }
+    n2v::build_alias_one(pr, m, N2V_SUM_NAIVE, work + lo,
+                         [&](uint32_t i, int32_t a) { out[lo + i].y = static_cast<int32_t>(lo) + a; });
+    for (uint32_t i = 0; i < m; ++i) {
+      const double p = pr[i];
+      if (p >= 1.0) out[lo + i].y = static_cast<int32_t>(lo + i);
+      out[lo + i].x = static_cast<int32_t>(neg_thr(p));
+    }
+  }
+}
+
+__global__ void sum_weights(const double* __restrict__ w, int64_t n, double* __restrict__ partial) {
+  // deterministic two-stage sum: one partial per block (fixed grid), added in block order by the caller kernel
+  __shared__ double sh[kBlock];
+  double acc = 0.0;
+  for (int64_t v = blockIdx.x * int64_t(kBlock) + threadIdx.x; v < n; v += int64_t(gridDim.x) * kBlock) acc += w[v];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = kBlock / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+__global__ void finish_sum(double* __restrict__ partial, int n_partial) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < n_partial; ++k) t += partial[k];
+    partial[0] = t;
   }
 }
 
@@ -143,8 +275,7 @@ extern "C" int n2v_sgns_prepare(const int64_t* counts, int64_t n_vertices, int64
   N2V_CHECK_ARG(n_vertices > 0 && n_vertices < (int64_t(1) << 31), "n2v_sgns_prepare: n_vertices out of range");
   N2V_CHECK_ARG(counts && keep_thr && neg_table && scratch, "n2v_sgns_prepare: NULL buffer");
   N2V_CHECK_ARG(sample >= 0.0, "n2v_sgns_prepare: negative sample");
-  double* probs = static_cast<double*>(scratch);
-  int32_t* work = reinterpret_cast<int32_t*>(probs + n_vertices);
+  double* probs = static_cast<double*>(scratch);   // count^ns_exponent per id
   unsigned long long* d_tot = nullptr;
   N2V_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_tot), 4 * sizeof(unsigned long long), stream));
   N2V_CUDA(cudaMemsetAsync(d_tot, 0, 4 * sizeof(unsigned long long), stream));
@@ -162,8 +293,38 @@ extern "C" int n2v_sgns_prepare(const int64_t* counts, int64_t n_vertices, int64
     n2v::set_error("n2v_sgns_prepare: no token reaches min_count=%lld (empty vocabulary)", static_cast<long long>(min_count));
     return N2V_ERR_INVALID;
   }
-  int* ok = reinterpret_cast<int*>(d_tot + 2);
-  neg_table_kernel<<<1, 32, 0, stream>>>(probs, n_vertices, work, neg_table, ok);
+  // scratch layout (T = n + top entries): [w f64 T | packed f64 T | ids i32 T]
+  const int64_t n_top = n2v_neg_top_entries(n_vertices);
+  const int64_t T = n_vertices + n_top;
+  double* packed = probs + T;
+  int32_t* ids = reinterpret_cast<int32_t*>(probs + 2 * T);
+  const double* level_w = probs;          // weights of the level the one-thread merge runs over
+  int64_t level_n = n_vertices;
+  int32_t* level_table = neg_table;
+  if (n_top > 0) {
+    // per-chunk tables in parallel; their masses become the top level's weights
+    double* mass = probs + n_vertices;
+    chunk_tables<<<grid_for(n_top), kBlock, 0, stream>>>(probs, n_vertices, ids, neg_table, mass);
+    N2V_LAUNCH_OK();
+    level_w = mass;
+    level_n = n_top;
+    level_table = neg_table + 2 * n_vertices;
+    packed = packed + n_vertices;          // disjoint from the region chunk_tables used
+    ids = ids + n_vertices;
+  }
+  // one table over `level_n` entries: scaled probs -> small / large streams -> one-warp Vose merge
+  double* partial = packed;                                                 // reused before scale_and_split fills it
+  const int sum_grid = grid_for(level_n);
+  sum_weights<<<sum_grid, kBlock, 0, stream>>>(level_w, level_n, partial);
+  N2V_LAUNCH_OK();
+  finish_sum<<<1, 32, 0, stream>>>(partial, sum_grid);
+  N2V_LAUNCH_OK();
+  double* d_total = reinterpret_cast<double*>(d_tot + 2);
+  N2V_CUDA(cudaMemcpyAsync(d_total, partial, sizeof(double), cudaMemcpyDeviceToDevice, stream));
+  N2V_CUDA(cudaMemsetAsync(d_tot, 0, 2 * sizeof(unsigned long long), stream));   // reuse as the two list counters
+  scale_and_split<<<grid_for(level_n), kBlock, 0, stream>>>(level_w, level_n, d_total, ids, packed, d_tot);
+  N2V_LAUNCH_OK();
+  vose_merge<<<1, 32, 0, stream>>>(ids, packed, level_n, d_tot, level_table);
   N2V_LAUNCH_OK();
   N2V_CUDA(cudaFreeAsync(d_tot, stream));
   return N2V_OK;

@@ -64,7 +64,8 @@ class KeyedVectors(object):
     # first access only (training never needs it).
     def _materialise(self):
         if self._lazy is not None:
-            ids, rank, counts, keep = self._lazy
+            ids, rank, counts, keep = (t.cpu().numpy() for t in self._lazy)
+            keep = keep.view(np.uint32)
             self._lazy = None
             self._vocab = {str(int(v)): Vocab(int(c), int(r), 2 ** 32 if k == 0xFFFFFFFF else int(k))
                            for v, r, c, k in zip(ids.tolist(), rank.tolist(), counts.tolist(), keep.tolist())}
@@ -193,24 +194,24 @@ class Word2Vec(object):
         if self.process_group is not None:
             n2v_dist.reduce_vocab(counts, first, self.process_group)
         self._keep = torch.empty(self._n_rows, dtype=torch.int32, device=dev)
-        self._neg = torch.empty((self._n_rows, 2), dtype=torch.int32, device=dev)
-        scratch = torch.empty(self._n_rows * 12 + 64, dtype=torch.uint8, device=dev)
+        n_top = (self._n_rows + 1023) // 1024 if self._n_rows > 65536 else 0      # n2v_neg_top_entries
+        self._neg = torch.empty((self._n_rows + n_top, 2), dtype=torch.int32, device=dev)
+        scratch = torch.empty((self._n_rows + n_top) * 20 + 64, dtype=torch.uint8, device=dev)
         totals = (C.c_int64 * 2)()
         _lib.check(lib.n2v_sgns_prepare(_lib.ptr(counts), self._n_rows, self.min_count, self.sample,
                                         self.ns_exponent, _lib.ptr(self._keep), _lib.ptr(self._neg),
                                         _lib.ptr(scratch), totals, stream), "n2v_sgns_prepare")
         self._retain_total, n_vocab = int(totals[0]), int(totals[1])
-        # wv.vocab: insertion order = first appearance in the corpus; .index = rank by count (desc, stable)
-        counts_h, first_h = counts.cpu().numpy(), first.cpu().numpy()
-        keep_h = self._keep.cpu().numpy().view(np.uint32)
-        ids = np.flatnonzero((counts_h > 0) & (counts_h >= self.min_count))
-        ids = ids[np.argsort(first_h[ids], kind="stable")]
-        rank = np.empty(len(ids), dtype=np.int64)
-        rank[np.argsort(-counts_h[ids], kind="stable")] = np.arange(len(ids))
-        self.wv._lazy = (ids, rank, counts_h[ids], keep_h[ids])
-        order = ids[np.argsort(rank)]
-        self._row_of_index = torch.as_tensor(order, device=dev)
-        assert n_vocab == len(ids)
+        # wv.vocab: insertion order = first appearance in the corpus; .index = rank by count (desc, ties by
+        # first appearance) -- computed with device sorts, kept on the device until somebody asks
+        ids = torch.nonzero((counts > 0) & (counts >= self.min_count)).view(-1)
+        ids = ids[torch.sort(first[ids], stable=True).indices]                 # first-appearance order
+        by_count = torch.sort(-counts[ids], stable=True).indices               # stable: ties keep that order
+        rank = torch.empty_like(by_count)
+        rank[by_count] = torch.arange(by_count.numel(), device=dev)
+        self.wv._lazy = (ids, rank, counts[ids], self._keep[ids])
+        self._row_of_index = ids[by_count]
+        assert n_vocab == int(ids.numel())
         # weights: reset_weights()
         self.syn0 = torch.empty((self._n_rows, self.vector_size), dtype=torch.float32, device=dev)
         self.syn1neg = torch.zeros((self._n_rows, self.vector_size), dtype=torch.float32, device=dev)

@@ -89,6 +89,51 @@ def test_negative_table_encodes_unigram_power(env):
     np.testing.assert_allclose(law[order], p_cum, atol=2e-9)
 
 
+def _alias_law(tab):
+    """Exact law encoded by an alias table of {thr u32, alias i32} entries (aliases index `tab`)."""
+    thr = tab[:, 0].view(np.uint32).astype(np.float64)
+    thr = np.where(thr == 4294967295.0, 4294967296.0, thr)
+    law = thr.copy()
+    np.add.at(law, tab[:, 1], 4294967296.0 - thr)
+    return law / law.sum()
+
+
+def test_two_level_negative_table_large_id_space(env):
+    """n_vertices > 65536: per-chunk alias tables + a top-level table over chunk masses must encode
+    count^0.75 exactly as the single table does (ids below min_count get probability 0)."""
+    import ctypes as C
+    from node2vec_b200 import _lib
+    torch = env.torch
+    lib = _lib.load()
+    n = 200_000 + 37                                   # last chunk is ragged
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    counts = (torch.rand(n, device="cuda", generator=gen).clamp_min(1e-4).pow(-0.6) * 2).long()
+    counts[1000:3100] = 0                              # two whole chunks (and a bit) of absent ids
+    n_top = (n + 1023) // 1024
+    keep = torch.empty(n, dtype=torch.int32, device="cuda")
+    neg = torch.empty((n + n_top, 2), dtype=torch.int32, device="cuda")
+    scratch = torch.empty((n + n_top) * 20 + 64, dtype=torch.uint8, device="cuda")
+    tot = (C.c_int64 * 2)()
+    _lib.check(lib.n2v_sgns_prepare(_lib.ptr(counts), n, 3, 1e-3, 0.75, _lib.ptr(keep), _lib.ptr(neg),
+                                    _lib.ptr(scratch), tot, _lib.current_stream_ptr()))
+    tab = neg.cpu().numpy()
+    c = counts.cpu().numpy().astype(np.float64)
+    w = np.where(c >= 3, c ** 0.75, 0.0)
+    top = _alias_law(tab[n:])
+    law = np.zeros(n)
+    for k in range(n_top):
+        lo, hi = k * 1024, min(n, (k + 1) * 1024)
+        if w[lo:hi].sum() == 0:
+            assert top[k] < 1e-12
+            continue
+        local = tab[lo:hi].copy()
+        assert ((local[:, 1] >= lo) & (local[:, 1] < hi)).all()      # aliases stay inside the chunk
+        local[:, 1] -= lo
+        law[lo:hi] = top[k] * _alias_law(local)
+    np.testing.assert_allclose(law, w / w.sum(), atol=1e-10)
+    assert int(tot[1]) == int((c >= 3).sum())
+
+
 @pytest.mark.parametrize("dim,atomic", [(32, True), (128, True), (128, False), (256, True), (100, True)])
 def test_kernel_arithmetic_matches_gensim_per_pair(env, dim, atomic):
     """Single-warp trace mode: the pairs the kernel sampled, re-applied sequentially with
