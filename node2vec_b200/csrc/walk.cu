@@ -32,7 +32,10 @@
 
 namespace {
 
-constexpr int kBlock = 256;
+#ifndef N2V_WALK_BLOCK
+#define N2V_WALK_BLOCK 256
+#endif
+constexpr int kBlock = N2V_WALK_BLOCK;
 #ifndef N2V_WALK_BLOCKS_PER_SM
 #define N2V_WALK_BLOCKS_PER_SM 6  // measured on B200 (v3 kernel): 6 blocks = 40 regs beats 8 (spills) and 5
 #endif
