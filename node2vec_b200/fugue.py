@@ -78,6 +78,18 @@ class WalkFrame(Frame):
     def as_array(self):
         return self.as_pandas().values.tolist()
 
+    def to_parquet(self, path: str) -> None:
+        """Write the [src, walk] frame as parquet (the reference's examples persist walks this way,
+        examples/fugue_spark.py:49-50) without building Python lists: `walk` is an Arrow
+        fixed-size list column backed by the walk matrix."""
+        import pyarrow as pa
+        import pyarrow.parquet as pq
+        w = np.ascontiguousarray(self.walks)
+        n, length = w.shape if w.ndim == 2 else (0, 1)
+        walk = pa.FixedSizeListArray.from_arrays(pa.array(w.reshape(-1), type=pa.int32()), length)
+        src = pa.array(w[:, 0].astype(np.int64) if n else np.zeros(0, dtype=np.int64))
+        pq.write_table(pa.table({"src": src, "walk": walk}), path)
+
     def count(self) -> int:
         return int(self.walks_device.shape[0])
 
@@ -87,6 +99,14 @@ class WalkFrame(Frame):
 
     def __len__(self):
         return self.count()
+
+
+def read_walks_parquet(path: str) -> pd.DataFrame:
+    """Read a [src, walk] parquet file (written by WalkFrame.to_parquet or by the reference's
+    pipeline) back into the pandas frame Node2VecGensim accepts."""
+    import pyarrow.parquet as pq
+    t = pq.read_table(path)
+    return pd.DataFrame({"src": t.column("src").to_numpy(), "walk": t.column("walk").to_pylist()})
 
 
 def _columns(df) -> list:

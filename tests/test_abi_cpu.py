@@ -173,3 +173,19 @@ def test_indexer_facade_bit_exact():
     e, vid = index_graph_dense(pd.DataFrame({"src": ["b", "a"], "dst": ["c", "b"]}), True)
     assert vid["id"].tolist() == [0, 1, 2] and vid["name"].tolist() == ["a", "b", "c"]
     assert e["src"].tolist() == [1, 0] and e["dst"].tolist() == [2, 1]
+
+
+def test_walk_frame_parquet_round_trip(tmp_path):
+    """The [src, walk] wire format (host logic only: a WalkFrame over a CPU tensor)."""
+    import numpy as np
+    import torch
+    from node2vec_b200.fugue import WalkFrame, read_walks_parquet
+    walks = np.array([[3, 1, 4, 1], [5, 9, 2, 6], [5, 3, 5, 8]], dtype=np.int32)
+    wf = WalkFrame(torch.as_tensor(walks))
+    assert wf.count() == 3 and wf.schema == ["src", "walk"]
+    df = wf.as_pandas()
+    assert df["src"].tolist() == [3, 5, 5] and df["walk"].tolist() == walks.tolist()
+    path = str(tmp_path / "walks.parquet")
+    wf.to_parquet(path)
+    back = read_walks_parquet(path)
+    assert back["src"].tolist() == [3, 5, 5] and back["walk"].tolist() == walks.tolist()
