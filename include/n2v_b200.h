@@ -281,7 +281,7 @@ int n2v_vocab_count(const int32_t* walks, int64_t n_walks, int32_t len, int64_t 
  *   neg_table    : alias table(s) over ids, P(v) ~ count^ns_exponent (0 for dropped ids), entries
  *                  {thr u32, alias i32}, n_vertices + n2v_neg_top_entries(n_vertices) of them.
  *                  n_vertices <= 65536: ONE table, one 8-byte gather per negative.  Larger: ids
- *                  are cut into chunks of 1024, each with its own alias table (built in parallel,
+ *                  are cut into chunks of 8192, each with its own alias table (built in parallel,
  *                  one thread per chunk), plus a top-level alias table over the chunk masses
  *                  stored after them: chunk ~ mass, then id within the chunk -- the same law
  *                  exactly, two gathers (the top level stays L2-resident).
@@ -291,7 +291,7 @@ int n2v_sgns_prepare(const int64_t* counts, int64_t n_vertices, int64_t min_coun
                      double ns_exponent, uint32_t* keep_thr, int32_t* neg_table, void* scratch,
                      int64_t* totals_host, void* stream);
 
-#define N2V_NEG_CHUNK 1024
+#define N2V_NEG_CHUNK 8192
 static inline N2V_HD int64_t n2v_neg_top_entries(int64_t n_vertices) {
   return n_vertices > 65536 ? (n_vertices + N2V_NEG_CHUNK - 1) / N2V_NEG_CHUNK : 0;
 }

@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(32) vose_merge(const int32_t* __restrict__ ids
   }
 }
 
-// ---- two-level table for large id spaces: one thread per 1024-id chunk --------------------------
+// ---- two-level table for large id spaces: one thread per N2V_NEG_CHUNK-id chunk --------------------------
 // chunk alias table (global ids as aliases) + the chunk's mass; same Vose core as the per-vertex
 // graph tables (alias_core.cuh), probs / work list in the caller's scratch
 __global__ void chunk_tables(double* __restrict__ probs, int64_t n, int32_t* __restrict__ work,

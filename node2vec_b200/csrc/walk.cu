@@ -199,7 +199,13 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
       const uint64_t walk_id = static_cast<uint64_t>(static_cast<uint32_t>(v)) * static_cast<uint32_t>(A.num_walks) + r;
       wid_lo = static_cast<uint32_t>(walk_id);
       wid_hi = static_cast<uint32_t>(walk_id >> 32);
-      enter(v, part_v, base_v, deg_v);
+      if (v >= 0 && v < g.n_vertices) {
+        enter(v, part_v, base_v, deg_v);
+      } else {   // a start id outside the graph has no adjacency row: dropped like a sink
+        part_v = 0;
+        base_v = 0;
+        deg_v = 0;
+      }
       t = -1;
       pos = 0;
       trial = 0;

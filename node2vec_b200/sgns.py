@@ -25,6 +25,12 @@ import torch
 from . import _lib, dist as n2v_dist
 
 _INT64_MAX = np.iinfo(np.int64).max
+NEG_CHUNK = 8192          # include/n2v_b200.h: N2V_NEG_CHUNK
+
+
+def neg_top_entries(n_rows: int) -> int:
+    """n2v_neg_top_entries(): entries of the top-level negative table (0 = single level)."""
+    return (n_rows + NEG_CHUNK - 1) // NEG_CHUNK if n_rows > 65536 else 0
 
 
 class Vocab(object):
@@ -194,7 +200,7 @@ class Word2Vec(object):
         if self.process_group is not None:
             n2v_dist.reduce_vocab(counts, first, self.process_group)
         self._keep = torch.empty(self._n_rows, dtype=torch.int32, device=dev)
-        n_top = (self._n_rows + 1023) // 1024 if self._n_rows > 65536 else 0      # n2v_neg_top_entries
+        n_top = neg_top_entries(self._n_rows)
         self._neg = torch.empty((self._n_rows + n_top, 2), dtype=torch.int32, device=dev)
         scratch = torch.empty((self._n_rows + n_top) * 20 + 64, dtype=torch.uint8, device=dev)
         totals = (C.c_int64 * 2)()

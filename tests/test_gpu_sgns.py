@@ -108,8 +108,10 @@ def test_two_level_negative_table_large_id_space(env):
     n = 200_000 + 37                                   # last chunk is ragged
     gen = torch.Generator(device="cuda").manual_seed(5)
     counts = (torch.rand(n, device="cuda", generator=gen).clamp_min(1e-4).pow(-0.6) * 2).long()
-    counts[1000:3100] = 0                              # two whole chunks (and a bit) of absent ids
-    n_top = (n + 1023) // 1024
+    counts[8000:25000] = 0                             # two whole chunks (and a bit) of absent ids
+    from node2vec_b200.sgns import NEG_CHUNK, neg_top_entries
+    n_top = neg_top_entries(n)
+    assert n_top == (n + NEG_CHUNK - 1) // NEG_CHUNK
     keep = torch.empty(n, dtype=torch.int32, device="cuda")
     neg = torch.empty((n + n_top, 2), dtype=torch.int32, device="cuda")
     scratch = torch.empty((n + n_top) * 20 + 64, dtype=torch.uint8, device="cuda")
@@ -122,7 +124,7 @@ def test_two_level_negative_table_large_id_space(env):
     top = _alias_law(tab[n:])
     law = np.zeros(n)
     for k in range(n_top):
-        lo, hi = k * 1024, min(n, (k + 1) * 1024)
+        lo, hi = k * NEG_CHUNK, min(n, (k + 1) * NEG_CHUNK)
         if w[lo:hi].sum() == 0:
             assert top[k] < 1e-12
             continue

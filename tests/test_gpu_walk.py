@@ -74,6 +74,14 @@ def test_csr_build_rejects_bad_ids(n2v):
         n2v.graph.DeviceGraph.from_arcs([0, 1, 7], [1, 0, 2], None, n_vertices=5)
 
 
+def test_start_ids_outside_the_graph_are_dropped(n2v):
+    g = n2v.graph.DeviceGraph.from_arcs([0, 1, 2], [1, 2, 0], None, n_vertices=3)
+    walks, alive, _ = g.walk(np.array([0, 7, -3, 2], dtype=np.int32), 2, 4, seed=1)
+    assert alive.cpu().tolist() == [True, True, False, False, False, False, True, True]
+    w = walks.cpu().numpy()
+    assert (w[2:6, 1:] == -1).all() and w[0].tolist() == [0, 1, 2, 0, 1]
+
+
 def test_empty_graph(n2v):
     g = n2v.graph.DeviceGraph.from_arcs(np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32), None, n_vertices=4)
     assert g.n_arcs == 0 and g.start_vertices().numel() == 0
