@@ -177,6 +177,28 @@ def cpu_baseline_walk(name, budget_s=12.0, procs=None):
                       f"adjacency prebuilt, Fugue joins and pickle/base64 decoding not included)"}
 
 
+def cpu_baseline_walk_c(name, budget_s=6.0):
+    """Same algorithm, C port (oracle/csrc/n2v_oracle.c: per walker per step it re-derives the biased
+    weights and rebuilds the alias table, like the reference) on all host cores -- context for how
+    much of the Python baseline is interpreter overhead."""
+    from oracle import clib
+    w = WORKLOADS[name]
+    src, dst = make_graph(name)
+    row_ptr, col, ws, _ = clib.csr_from_arcs(src, dst, None, w["n"])
+    starts = np.flatnonzero(np.diff(row_ptr) > 0).astype(np.int32)
+    threads = os.cpu_count() or 1
+    steps, dt, nw = 0, 0.0, 1
+    while dt < budget_s and nw <= w["num_walks"]:
+        t0 = time.perf_counter()
+        walks, alive = clib.reference_walk(row_ptr, col, ws, starts, nw, w["walk_length"], w["p"], w["q"], "naive",
+                                           None, threads=threads)
+        dt += time.perf_counter() - t0
+        steps += int(alive.sum()) * w["walk_length"]
+        nw *= 2
+    return {"value": steps / dt, "unit": "walk-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} steps in {dt:.1f}s, {threads} threads (C port of the reference's per-row algorithm)"}
+
+
 _ADJ = None
 
 
@@ -553,8 +575,9 @@ def main():
     if sgns:
         sgns.pop("gpu_launches")
         line["sgns"] = sgns
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only (contract)
         line["cpu_baseline"] = cpu_baseline_walk(name)
+        line["cpu_baseline_c"] = cpu_baseline_walk_c(name)
         if sgns:
             sample = host_out.numpy()
             line["sgns"]["cpu_baseline"] = cpu_baseline_sgns(sample, w["n"], w["dim"])

@@ -35,8 +35,11 @@ def blogcatalog_like(n: int = 10000, m: int = 334000, seed: int = 42) -> Tuple[n
     max degree ~1.7k).  Cached under /tmp because the generator takes a few seconds."""
     cache = f"/tmp/n2v_blogcatalog_like_{n}_{m}_{seed}.npz"
     if os.path.exists(cache):
-        z = np.load(cache)
-        return z["src"], z["dst"]
+        try:
+            z = np.load(cache)
+            return z["src"], z["dst"]
+        except (OSError, ValueError, KeyError):
+            pass
     import networkx as nx
     g = nx.powerlaw_cluster_graph(n, 34, 0.3, seed=seed)
     e = np.array(g.edges(), dtype=np.int64)
@@ -57,8 +60,10 @@ def blogcatalog_like(n: int = 10000, m: int = 334000, seed: int = 42) -> Tuple[n
                 drop -= 1
         e = e[keep]
     src, dst = _symmetrise(e[:, 0], e[:, 1])
-    try:
-        np.savez(cache, src=src, dst=dst)
+    try:   # atomic publish: several ranks may generate the same graph at the same time
+        tmp = f"{cache}.{os.getpid()}.tmp.npz"
+        np.savez(tmp, src=src, dst=dst)
+        os.replace(tmp, cache)
     except OSError:
         pass
     return src, dst

@@ -189,3 +189,20 @@ def test_walk_frame_parquet_round_trip(tmp_path):
     wf.to_parquet(path)
     back = read_walks_parquet(path)
     assert back["src"].tolist() == [3, 5, 5] and back["walk"].tolist() == walks.tolist()
+
+
+def test_walk_matrix_inputs_host_logic():
+    """What Node2VecGensim hands the SGNS engine: decimal-string tokens (embedding.py:125), ints, tensors;
+    ragged walks are rejected (the reference's np.array(...) would not build a matrix either)."""
+    import numpy as np
+    import torch
+    from node2vec_b200.sgns import _walk_matrix, neg_top_entries, NEG_CHUNK
+    cpu = torch.device("cpu")
+    a = _walk_matrix(np.array([["3", "1", "4"], ["1", "5", "9"]]), cpu)
+    assert a.dtype == torch.int32 and a.tolist() == [[3, 1, 4], [1, 5, 9]]
+    assert _walk_matrix([[1, 2], [3, 4]], cpu).tolist() == [[1, 2], [3, 4]]
+    t = torch.tensor([[7, 8, 9]], dtype=torch.int64)
+    assert _walk_matrix(t, cpu).dtype == torch.int32
+    with pytest.raises(ValueError):
+        _walk_matrix([[1, 2, 3], [4, 5]], cpu)
+    assert neg_top_entries(65536) == 0 and neg_top_entries(65537) == 9 and neg_top_entries(1 << 26) == (1 << 26) // NEG_CHUNK
