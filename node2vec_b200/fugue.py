@@ -8,6 +8,7 @@ duck-typed: a pandas DataFrame, anything exposing ``.as_pandas()`` (Fugue
 of torch tensors / numpy arrays ``(src, dst[, weight])``.
 """
 import logging
+import os
 from typing import Any, Dict, Optional, Tuple
 
 import numpy as np
@@ -193,6 +194,46 @@ def _graph_arrays(df_graph):
     return df["src"].to_numpy(), df["dst"].to_numpy(), weight
 
 
+_SEED_LAYER_MIX = 0x9E3779B97F4A7C15   # odd 64-bit constant: layer k walks under seed + k * MIX (mod 2^64)
+
+
+def _walk_from_seed_ids(graph, start, walk_seed, num_walks, walk_length, p, q, random_seed, collect_stats):
+    """``walk_start.inner_join(walk_seed)`` (fugue.py:133-134): rows stay in ascending-id order and an
+    id listed k times in ``walk_seed`` starts k x num_walks independent walkers (the reference's own
+    test feeds duplicated ids, tests/test_fugue.py:73-75).  A walker's Philox stream is keyed by
+    (seed, start vertex, walk number), so the k-th copy of an id runs as layer k under a derived seed;
+    layers are merged back into the join's row order on the device."""
+    ids, mult = np.unique(_to_pandas(walk_seed)["id"].to_numpy().astype(np.int64), return_counts=True)
+    dev = start.device
+    ids_t = torch.as_tensor(ids, device=dev)
+    mult_t = torch.as_tensor(mult, device=dev)
+    start64 = start.to(torch.int64)
+    pos = torch.searchsorted(ids_t, start64).clamp_(max=max(int(ids_t.numel()) - 1, 0))
+    hit = (ids_t[pos] == start64) if ids_t.numel() else torch.zeros_like(start64, dtype=torch.bool)
+    start, m = start[hit], mult_t[pos[hit]]
+    layers = int(m.max().item()) if m.numel() else 1
+    if random_seed is None:
+        random_seed = int.from_bytes(os.urandom(8), "little")
+    if layers <= 1:
+        walks, alive, stats = graph.walk(start, num_walks, walk_length, p, q, random_seed, collect_stats)
+        return (walks[alive] if not bool(alive.all()) else walks), stats
+    rank = torch.arange(start.numel(), device=dev, dtype=torch.int64)
+    r = torch.arange(num_walks, device=dev, dtype=torch.int64)
+    parts, keys, stats = [], [], None
+    for k in range(layers):
+        sel = m > k
+        w, alive, st = graph.walk(start[sel], num_walks, walk_length, p, q,
+                                  (random_seed + k * _SEED_LAYER_MIX) & 0xFFFFFFFFFFFFFFFF, collect_stats)
+        key = ((rank[sel] * layers + k) * num_walks).view(-1, 1) + r.view(1, -1)
+        alive = alive.view(-1).bool()
+        parts.append(w[alive])
+        keys.append(key.view(-1)[alive])
+        if st is not None:
+            stats = st if stats is None else {n: stats[n] + st[n] for n in st}
+    order = torch.argsort(torch.cat(keys))
+    return torch.cat(parts)[order], stats
+
+
 def random_walk(
     compute_engine: Any,
     df_graph: Any,
@@ -234,11 +275,11 @@ def random_walk(
         src, dst, weight = _graph_arrays(df_graph)
         graph = DeviceGraph.from_arcs(src, dst, weight)
     start = graph.start_vertices()
-    if walk_seed is not None:
-        ids = torch.as_tensor(np.unique(_to_pandas(walk_seed)["id"].to_numpy().astype(np.int64)),
-                              device=start.device)
-        start = start[torch.isin(start.to(torch.int64), ids)]
-    walks, alive, stats = graph.walk(start, num_walks, walk_length, p, q, random_seed, collect_stats)
-    walks = walks[alive] if not bool(alive.all()) else walks
+    if walk_seed is None:
+        walks, alive, stats = graph.walk(start, num_walks, walk_length, p, q, random_seed, collect_stats)
+        walks = walks[alive] if not bool(alive.all()) else walks
+    else:
+        walks, stats = _walk_from_seed_ids(graph, start, walk_seed, num_walks, walk_length, p, q, random_seed,
+                                           collect_stats)
     logging.info("random_walk(): random walking done ...")
     return WalkFrame(walks, stats=stats)

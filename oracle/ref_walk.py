@@ -5,7 +5,9 @@ Restates, function by function, what ``node2vec/randomwalk.py`` and the step loo
 ``oracle/csrc/n2v_oracle.c`` covers the big ones).  Each function cites the reference
 lines it follows.  Pinned against the reference by ``tests/test_oracle_golden.py``
 using fixtures that ``tests/golden/make_golden.py`` produced by importing the
-unmodified reference.
+unmodified reference -- its transformer functions directly (``walks.json``) and its entry
+points ``node2vec.fugue.random_walk`` / ``trim_index`` verbatim on a pandas stand-in for
+Fugue (``fugue_verbatim.json``, ``tests/golden/fugue_shim``).
 
 A note on ``sum()``: the reference divides by ``sum(node_weights) / n``
 (``randomwalk.py:172``).  On the interpreters the reference supports (3.6/3.7,
@@ -238,8 +240,12 @@ def random_walk(
     adj = build_adjacency(src, dst, wt)
     starts = sorted(adj)
     if walk_seed is not None:
-        keep = set(int(s) for s in walk_seed)
-        starts = [v for v in starts if v in keep]
+        # inner join on id: left (ascending id) order, one row per matching seed row -- a seed id
+        # listed k times starts k x num_walks walkers (tests/test_fugue.py:73-75 does exactly that)
+        mult: Dict[int, int] = {}
+        for s in walk_seed:
+            mult[int(s)] = mult.get(int(s), 0) + 1
+        starts = [v for v in starts for _ in range(mult.get(v, 0))]
     rows = start_rows(starts, int(n2v_params["num_walks"]))
     p, q = n2v_params["return_param"], n2v_params["inout_param"]
     for _ in range(int(n2v_params["walk_length"])):

@@ -312,6 +312,55 @@ def gen_trim(rng):
     return {"src": src, "dst": dst, "weight": hx(wt), "cases": cases}
 
 
+def gen_fugue_verbatim(rng):
+    """The reference's OWN entry points, node2vec.fugue.trim_index / random_walk, run verbatim on
+    the pandas stand-in for Fugue under tests/golden/fugue_shim (Fugue is not installable here)."""
+    sys.path.insert(0, os.path.join(HERE, "fugue_shim"))
+    import_reference_indexer()                      # pyspark stub + DataFrame.append shim
+    from fugue import ArrayDataFrame, NativeExecutionEngine, PandasDataFrame
+    import node2vec.fugue as ref_fugue
+    graphs = small_graphs(random.Random(7))
+    walks = []
+    settings = [
+        ("ref_test_graph", {"num_walks": 2, "walk_length": 3, "return_param": 0.5}, None, 7),
+        ("ref_test_graph", {"num_walks": 2, "walk_length": 4, "return_param": 0.5}, [0, 0, 3, 2, 4, 4], 7),  # tests/test_fugue.py:73-75: duplicated seeds
+        ("sink_multi", {"num_walks": 4, "walk_length": 6, "return_param": 0.5, "inout_param": 2.0}, None, 13),
+        ("er40_weighted", {"num_walks": 2, "walk_length": 10, "return_param": 0.25, "inout_param": 4.0}, list(range(0, 40, 3)), 21),
+        ("sparse_directed", {"num_walks": 3, "walk_length": 5, "return_param": 2.0, "inout_param": 0.5}, None, 1),
+    ]
+    for name, params, seeds, seed in settings:
+        s, d, w = graphs[name]
+        rec = {"graph": name, "src": s, "dst": d, "weight": hx(w), "params": dict(params), "walk_seed": seeds,
+               "random_seed": seed}
+        for label in ("native", "naive"):
+            with sum_mode(label):
+                df = PandasDataFrame(pd.DataFrame({"src": s, "dst": d, "weight": w}))
+                sd = None if seeds is None else PandasDataFrame(pd.DataFrame({"id": seeds}))
+                p = dict(params)
+                res = ref_fugue.random_walk(NativeExecutionEngine(), df, p, sd, random_seed=seed).as_pandas()
+            rec[label] = {"src": [int(x) for x in res["src"]], "walk": [list(map(int, x)) for x in res["walk"]]}
+            rec["params_after"] = p                 # defaults merged into the caller's dict in place
+        walks.append(rec)
+    # trim_index: the reference's own test inputs (tests/test_fugue.py:13-56) plus a seeded trim
+    trims = []
+    graph = [[0, 2, 0.41], [0, 4, 0.85], [3, 4, 0.36], [2, 0, 0.68], [4, 0, 0.1], [4, 3, 0.37]]
+    for kwargs in ({"indexed": True}, {"indexed": True, "max_out_deg": 1, "random_seed": 5}):
+        df = ArrayDataFrame(graph, schema="src:int,dst:int,weight:double")
+        r, nid = ref_fugue.trim_index(NativeExecutionEngine(), df, **kwargs)
+        rp = r.as_pandas()
+        trims.append({"input": {"src": [g[0] for g in graph], "dst": [g[1] for g in graph], "weight": [g[2] for g in graph]},
+                      "kwargs": kwargs, "src": [int(x) for x in rp["src"]], "dst": [int(x) for x in rp["dst"]],
+                      "weight": hx(rp["weight"]), "name_id": None})
+    dat1 = {"src": ["a1", "a1", "a1", "a2", "b2"], "dst": ["a2", "b1", "b2", "b1", "a2"]}
+    for kwargs in ({"indexed": False}, {"indexed": False, "directed": False}, {"indexed": False, "max_out_deg": 2, "random_seed": 3}):
+        r, nid = ref_fugue.trim_index(NativeExecutionEngine(), PandasDataFrame(pd.DataFrame(dat1)), **kwargs)
+        rp, npd = r.as_pandas(), nid.as_pandas()
+        trims.append({"input": dat1, "kwargs": kwargs, "src": [int(x) for x in rp["src"]], "dst": [int(x) for x in rp["dst"]],
+                      "weight": hx(rp["weight"]),
+                      "name_id": {"vertex_id": [int(x) for x in npd["vertex_id"]], "vertex_name": list(npd["vertex_name"])}})
+    return {"native_sum_mode": native_mode_name(), "walks": walks, "trim_index": trims}
+
+
 def main():
     rng = random.Random(20261017)
     files = {
@@ -321,6 +370,7 @@ def main():
         "walks.json": gen_walks(rng),
         "indexer.json": gen_indexer(rng),
         "trim.json": gen_trim(rng),
+        "fugue_verbatim.json": gen_fugue_verbatim(rng),
     }
     meta = {"python": sys.version.split()[0], "pandas": pd.__version__, "numpy": np.__version__,
             "reference": "graph-embedding/node2vec 0.3.5 (node2vec-fugue), imported from " + REF}

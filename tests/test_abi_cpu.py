@@ -175,6 +175,25 @@ def test_indexer_facade_bit_exact():
     assert e["src"].tolist() == [1, 0] and e["dst"].tolist() == [2, 1]
 
 
+def test_trim_index_facade_matches_verbatim_reference():
+    """node2vec_b200.fugue.trim_index (host pandas code) against node2vec.fugue.trim_index outputs
+    recorded by tests/golden/make_golden.py::gen_fugue_verbatim."""
+    from node2vec_b200.fugue import trim_index
+    from tests.helpers import load_golden
+    for c in load_golden("fugue_verbatim.json")["trim_index"]:
+        inp = dict(c["input"])
+        res, name_id = trim_index(None, pd.DataFrame(inp), **c["kwargs"])
+        out = res.as_pandas()
+        assert out["src"].tolist() == c["src"] and out["dst"].tolist() == c["dst"], c["kwargs"]
+        assert [float(x).hex() for x in out["weight"]] == c["weight"]
+        if c["name_id"] is None:
+            assert name_id is None
+        else:
+            nid = name_id.as_pandas()
+            assert nid["vertex_id"].tolist() == c["name_id"]["vertex_id"]
+            assert nid["vertex_name"].tolist() == c["name_id"]["vertex_name"]
+
+
 def test_walk_frame_parquet_round_trip(tmp_path):
     """The [src, walk] wire format (host logic only: a WalkFrame over a CPU tensor)."""
     import numpy as np

@@ -430,6 +430,18 @@ def test_random_walk_facade_reference_graph(n2v):
     seeds = pd.DataFrame({"id": [0, 4, 99]})
     res = n2v.fugue.random_walk(None, n2v.fugue.Frame(df), params, seeds, random_seed=3)
     assert sorted(set(res.as_pandas()["src"])) == [0, 4] and res.count() == 4
+    # duplicated seed ids multiply walkers, rows in the inner join's order (tests/test_fugue.py:73-75;
+    # tests/golden/fugue_verbatim.json records the unmodified reference doing so)
+    dup = pd.DataFrame({"id": [0, 0, 3, 2, 4, 4, 4]})
+    r1 = n2v.fugue.random_walk(None, df, dict(params), dup, random_seed=3).walks
+    assert r1[:, 0].tolist() == [0] * 4 + [2] * 2 + [3] * 2 + [4] * 6
+    r2 = n2v.fugue.random_walk(None, df, dict(params), dup, random_seed=3).walks
+    assert np.array_equal(r1, r2)
+    one = n2v.fugue.random_walk(None, df, dict(params), pd.DataFrame({"id": [0, 2, 3, 4]}), random_seed=3).walks
+    assert np.array_equal(r1[[0, 1, 4, 5, 6, 7, 8, 9]], one)           # layer 0 is the plain run
+    big = n2v.fugue.random_walk(None, df, {"num_walks": 200, "walk_length": 6}, pd.DataFrame({"id": [4, 4]}),
+                                random_seed=5).walks
+    assert big.shape[0] == 400 and not np.array_equal(big[:200], big[200:])   # copies are independent walkers
     with pytest.raises(ValueError):
         n2v.fugue.random_walk(None, df, params, df)                     # walk_seed without "id"
     with pytest.raises(ValueError):

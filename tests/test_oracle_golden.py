@@ -187,3 +187,51 @@ def test_trim_hotspot_matches_reference():
         assert df["src"].tolist() == c["src"]
         assert df["dst"].tolist() == c["dst"]
         assert [x.hex() for x in df["weight"].tolist()] == c["weight"]
+
+
+# ---- the reference's own entry points, run verbatim on the Fugue stand-in ------------
+@pytest.mark.parametrize("label", ["native", "naive"])
+def test_verbatim_fugue_random_walk(label):
+    """fugue_verbatim.json holds node2vec.fugue.random_walk outputs (the real DAG code: joins,
+    per-step re-seeding, sink drops, duplicated walk_seed ids); the oracle must reproduce them."""
+    fx = load_golden("fugue_verbatim.json")
+    mode = _mode_of(fx, label)
+    assert len(fx["walks"]) >= 5
+    for rec in fx["walks"]:
+        params = dict(rec["params"])
+        for k, v in {"num_walks": 30, "walk_length": 10, "return_param": 1.0, "inout_param": 1.0}.items():
+            params.setdefault(k, v)                              # constants.py:9-18
+        assert params == rec["params_after"]
+        got = ref_walk.random_walk(rec["src"], rec["dst"], unhex(rec["weight"]), params, rec["walk_seed"],
+                                   rec["random_seed"], sum_mode=mode, rng=random.Random())
+        assert got == rec[label]["walk"], rec["graph"]
+        assert [w[0] for w in got] == rec[label]["src"]
+
+
+def test_verbatim_fugue_duplicate_seed_multiplicity():
+    fx = load_golden("fugue_verbatim.json")
+    rec = next(r for r in fx["walks"] if r["walk_seed"] and len(set(r["walk_seed"])) < len(r["walk_seed"]))
+    heads = [w[0] for w in rec["naive"]["walk"]]
+    nw = rec["params"]["num_walks"]
+    assert heads == [v for v in sorted(set(rec["walk_seed"])) for _ in range(rec["walk_seed"].count(v) * nw)]
+
+
+def test_verbatim_fugue_trim_index():
+    """trim_index = trim per src partition FIRST (on the raw names, fugue.py:57-67), THEN index
+    (fugue.py:69-77)."""
+    fx = load_golden("fugue_verbatim.json")
+    assert len(fx["trim_index"]) >= 5
+    for c in fx["trim_index"]:
+        kw, inp = c["kwargs"], c["input"]
+        has_w = "weight" in inp
+        wt = inp["weight"] if has_w else [1.0] * len(inp["src"])
+        df = ref_indexer.trim_hotspot(inp["src"], inp["dst"], wt, kw.get("max_out_deg", 0), kw.get("random_seed"))
+        s, d, w = df["src"].tolist(), df["dst"].tolist(), df["weight"].to_numpy(dtype=np.float64)
+        if kw["indexed"]:
+            assert c["name_id"] is None
+        else:
+            s, d, w, names, ids = ref_indexer.index_graph(s, d, w if has_w else None, kw.get("directed", True))
+            assert c["name_id"] == {"vertex_id": ids.tolist(), "vertex_name": names}
+            s, d = s.tolist(), d.tolist()
+        assert s == c["src"] and d == c["dst"], kw
+        assert [float(x).hex() for x in np.asarray(w).tolist()] == c["weight"]
