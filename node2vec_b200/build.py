@@ -48,5 +48,28 @@ def build_library(force: bool = False, extra_flags=(), verbose: bool = False) ->
     return SO
 
 
+EXAMPLE_SRC = os.path.join(HERE, "..", "examples", "c_consumer.c")
+EXAMPLE_BIN = os.path.join(HERE, "..", "examples", "_build", "c_consumer")
+
+
+def build_c_consumer(force: bool = False) -> str:
+    """examples/c_consumer.c: a plain-C11 program that drives the hot path through the C ABI alone
+    (gcc, not nvcc: the header must be consumable by a C compiler, as a cgo/JNI binding would)."""
+    so = build_library()
+    if not force and os.path.exists(EXAMPLE_BIN) and os.path.getmtime(EXAMPLE_BIN) >= max(
+            os.path.getmtime(EXAMPLE_SRC), os.path.getmtime(so)):
+        return EXAMPLE_BIN
+    cuda = os.path.dirname(os.path.dirname(_nvcc()))
+    os.makedirs(os.path.dirname(EXAMPLE_BIN), exist_ok=True)
+    subprocess.check_call([
+        "gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-O2", EXAMPLE_SRC,
+        "-I", os.path.join(HERE, "..", "include"), "-I", os.path.join(cuda, "include"),
+        "-L", CSRC, "-ln2v_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart",
+        "-Wl,-rpath,$ORIGIN/../../node2vec_b200/csrc", "-Wl,-rpath," + os.path.join(cuda, "lib64"),
+        "-o", EXAMPLE_BIN])
+    return EXAMPLE_BIN
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))
+    print(build_c_consumer(force="--force" in sys.argv))

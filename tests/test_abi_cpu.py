@@ -39,6 +39,21 @@ def test_abi_version_and_struct_sizes(lib):
     assert C.sizeof(_lib.WalkConsts) == 40
 
 
+def test_header_is_plain_c_and_c_consumer_links():
+    """The boundary is a C ABI: the header must compile as C11 with all warnings as errors, and a
+    C program using every walk-path entry point must link against the library (it RUNS in the gpu
+    suite, tests/test_gpu_walk.py::test_plain_c_consumer)."""
+    import subprocess
+    from node2vec_b200 import build as nb
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-x", "c",
+                           os.path.join(root, "include", "n2v_b200.h")])
+    exe = nb.build_c_consumer(force=True)
+    assert os.access(exe, os.X_OK)
+    needed = subprocess.check_output(["readelf", "-d", exe], text=True)
+    assert "libn2v_b200.so" in needed and "python" not in needed.lower() and "torch" not in needed.lower()
+
+
 def test_walk_consts_host_only(lib):
     from node2vec_b200 import graph
     from oracle import clib

@@ -454,6 +454,20 @@ def test_random_walk_facade_reference_graph(n2v):
     assert np.array_equal(a, b) and not np.array_equal(c, d)
 
 
+def test_plain_c_consumer():
+    """examples/c_consumer.c: CSR + hash + alias build and a walk driven from plain C through the C
+    ABI only (no Python, no torch in the process); it validates every hop on the host itself."""
+    import subprocess
+    from node2vec_b200 import build as nb
+    exe = nb.build_c_consumer()
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr + out.stdout
+    assert out.stdout.startswith("c_consumer OK abi=5") and "dropped_at_sink=" in out.stdout
+    fields = dict(kv.split("=") for kv in out.stdout.split()[2:])
+    assert int(fields["walkers"]) == 999 * 4 and int(fields["alive"]) + int(fields["dropped_at_sink"]) == 999 * 4
+    assert int(fields["dropped_at_sink"]) > 0 and int(fields["alive"]) > 0
+
+
 def test_random_walk_drops_walkers_at_sinks(n2v):
     import pandas as pd
     fx = [r for r in load_golden("walks.json")["walks"] if r["graph"] == "sink_multi"][0]
