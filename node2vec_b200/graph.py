@@ -15,16 +15,21 @@ import torch
 from . import _lib
 
 
-def _as_device_i32(x, device) -> torch.Tensor:
+def _as_device(x, device, np_dtype, torch_dtype) -> torch.Tensor:
     if isinstance(x, torch.Tensor):
-        return x.to(device=device, dtype=torch.int32).contiguous()
-    return torch.as_tensor(np.ascontiguousarray(x).astype(np.int32, copy=False), device=device)
+        return x.to(device=device, dtype=torch_dtype).contiguous()
+    arr = np.ascontiguousarray(x).astype(np_dtype, copy=False)
+    if not arr.flags.writeable:          # pandas >= 3 hands out read-only views; torch wants writable memory
+        arr = arr.copy()
+    return torch.as_tensor(arr, device=device)
+
+
+def _as_device_i32(x, device) -> torch.Tensor:
+    return _as_device(x, device, np.int32, torch.int32)
 
 
 def _as_device_f64(x, device) -> torch.Tensor:
-    if isinstance(x, torch.Tensor):
-        return x.to(device=device, dtype=torch.float64).contiguous()
-    return torch.as_tensor(np.ascontiguousarray(x).astype(np.float64, copy=False), device=device)
+    return _as_device(x, device, np.float64, torch.float64)
 
 
 class DeviceGraph:

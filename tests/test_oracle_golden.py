@@ -199,8 +199,8 @@ def test_verbatim_fugue_random_walk(label):
     assert len(fx["walks"]) >= 5
     for rec in fx["walks"]:
         params = dict(rec["params"])
-        for k, v in {"num_walks": 30, "walk_length": 10, "return_param": 1.0, "inout_param": 1.0}.items():
-            params.setdefault(k, v)                              # constants.py:9-18
+        for k, v in {"num_walks": 10, "walk_length": 20, "return_param": 1.0, "inout_param": 1.0}.items():
+            params.setdefault(k, v)                              # constants.py:15-20
         assert params == rec["params_after"]
         got = ref_walk.random_walk(rec["src"], rec["dst"], unhex(rec["weight"]), params, rec["walk_seed"],
                                    rec["random_seed"], sum_mode=mode, rng=random.Random())
