@@ -513,9 +513,10 @@ def main():
     seeds_df = _IdFrame(start.cpu().numpy()) if world > 1 else None
 
     def e2e_pass():
-        res = fugue.random_walk(None, (src_pin, dst_pin), dict(params), seeds_df, random_seed=seed)
-        host_out.copy_(res.walks_device, non_blocking=True)
+        # out=: rows land in the pinned host matrix, D2H of chunk k overlapped with the kernel of chunk k+1
+        res = fugue.random_walk(None, (src_pin, dst_pin), dict(params), seeds_df, random_seed=seed, out=host_out)
         torch.cuda.synchronize()
+        assert res.walks.shape == (W, w["walk_length"] + 1) and res.walks[0, 0] >= 0
         return res
 
     e2e_pass()

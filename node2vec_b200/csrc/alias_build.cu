@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(kHubBlock)
 alias_hub_kernel(n2v_vertex_t* __restrict__ vtx, const n2v_vertex_t* lookup, const int32_t* __restrict__ col,
                  const double* __restrict__ weight, int sum_mode, int32_t* __restrict__ alias,
                  double* __restrict__ probs, n2v_arc_t* __restrict__ arcs, const int32_t* __restrict__ hubs,
-                 unsigned int n_hubs, unsigned long long* __restrict__ n_zero) {
+                 const unsigned int* __restrict__ n_hubs_ptr, unsigned long long* __restrict__ n_zero) {
+  const unsigned int n_hubs = *n_hubs_ptr;   // written by alias_build_kernel earlier on the same stream
   extern __shared__ __align__(16) unsigned char hub_smem[];
   __shared__ double s_mean;
   __shared__ int s_counts[kHubBlock + 1];
@@ -303,15 +304,14 @@ extern "C" int n2v_alias_build(n2v_vertex_t* vtx, const n2v_vertex_t* vtx_lookup
                                                                    sum_mode, alias, probs, arcs, scratch, d_zero,
                                                                    d_hubs, d_nhubs);
   N2V_LAUNCH_OK();
-  unsigned int n_hubs = 0;
-  N2V_CUDA(cudaMemcpyAsync(&n_hubs, d_nhubs, sizeof(n_hubs), cudaMemcpyDeviceToHost, stream));
-  N2V_CUDA(cudaStreamSynchronize(stream));
-  if (n_hubs > 0) {
+  if (n_arcs >= kHubMin) {
+    // the hub count stays on the device (no host round trip): one CTA per SM strides over the list and
+    // exits at once when it is empty
     const size_t smem = static_cast<size_t>(kHubMax) * 16;
     N2V_CUDA(cudaFuncSetAttribute(alias_hub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    const unsigned int grid = n_hubs < static_cast<unsigned int>(n2v::kSmCount) ? n_hubs : n2v::kSmCount;
-    alias_hub_kernel<<<grid, kHubBlock, smem, stream>>>(vtx, lookup, col, weight_sorted, sum_mode, alias, probs,
-                                                        arcs, d_hubs, n_hubs, d_zero);
+    const int64_t grid = max_hubs < n2v::kSmCount ? max_hubs : n2v::kSmCount;
+    alias_hub_kernel<<<static_cast<unsigned int>(grid), kHubBlock, smem, stream>>>(
+        vtx, lookup, col, weight_sorted, sum_mode, alias, probs, arcs, d_hubs, d_nhubs, d_zero);
     N2V_LAUNCH_OK();
   }
   unsigned long long h = 0;

@@ -16,7 +16,7 @@ import pandas as pd
 import torch
 
 from .constants import MAX_OUT_DEGREES, NODE2VEC_PARAMS
-from .graph import DeviceGraph
+from .graph import DeviceGraph, walk_to_host
 from .indexer import index_graph_pandas
 
 
@@ -194,10 +194,30 @@ def _graph_arrays(df_graph):
     return df["src"].to_numpy(), df["dst"].to_numpy(), weight
 
 
+def _walk_rows(graph, start, num_walks, walk_length, p, q, random_seed, collect_stats, out):
+    """One walk over ``start``; rows of dropped walkers removed.  Returns (device rows, host rows or
+    None, stats).  With ``out`` (pinned host matrix) the copy is pipelined with the kernel."""
+    if out is None or collect_stats:
+        walks, alive, stats = graph.walk(start, num_walks, walk_length, p, q, random_seed, collect_stats)
+        walks = walks[alive] if not bool(alive.all()) else walks
+        if out is None:
+            return walks, None, stats
+        out[: walks.shape[0]].copy_(walks)
+        return walks, out.numpy()[: walks.shape[0]], stats
+    walks, alive = walk_to_host(graph, start, num_walks, walk_length, p, q, random_seed, out)
+    host = out.numpy()[: walks.shape[0]]
+    if not bool(alive.all()):
+        keep = alive.cpu().numpy()
+        n = int(keep.sum())
+        host[:n] = host[keep]                     # compact in place (boolean indexing copies first)
+        walks, host = walks[alive], host[:n]
+    return walks, host, None
+
+
 _SEED_LAYER_MIX = 0x9E3779B97F4A7C15   # odd 64-bit constant: layer k walks under seed + k * MIX (mod 2^64)
 
 
-def _walk_from_seed_ids(graph, start, walk_seed, num_walks, walk_length, p, q, random_seed, collect_stats):
+def _walk_from_seed_ids(graph, start, walk_seed, num_walks, walk_length, p, q, random_seed, collect_stats, out=None):
     """``walk_start.inner_join(walk_seed)`` (fugue.py:133-134): rows stay in ascending-id order and an
     id listed k times in ``walk_seed`` starts k x num_walks independent walkers (the reference's own
     test feeds duplicated ids, tests/test_fugue.py:73-75).  A walker's Philox stream is keyed by
@@ -215,8 +235,7 @@ def _walk_from_seed_ids(graph, start, walk_seed, num_walks, walk_length, p, q, r
     if random_seed is None:
         random_seed = int.from_bytes(os.urandom(8), "little")
     if layers <= 1:
-        walks, alive, stats = graph.walk(start, num_walks, walk_length, p, q, random_seed, collect_stats)
-        return (walks[alive] if not bool(alive.all()) else walks), stats
+        return _walk_rows(graph, start, num_walks, walk_length, p, q, random_seed, collect_stats, out)
     rank = torch.arange(start.numel(), device=dev, dtype=torch.int64)
     r = torch.arange(num_walks, device=dev, dtype=torch.int64)
     parts, keys, stats = [], [], None
@@ -231,7 +250,11 @@ def _walk_from_seed_ids(graph, start, walk_seed, num_walks, walk_length, p, q, r
         if st is not None:
             stats = st if stats is None else {n: stats[n] + st[n] for n in st}
     order = torch.argsort(torch.cat(keys))
-    return torch.cat(parts)[order], stats
+    walks = torch.cat(parts)[order]
+    if out is None:
+        return walks, None, stats
+    out[: walks.shape[0]].copy_(walks)
+    return walks, out.numpy()[: walks.shape[0]], stats
 
 
 def random_walk(
@@ -244,6 +267,7 @@ def random_walk(
     *,
     graph: Optional[DeviceGraph] = None,
     collect_stats: bool = False,
+    out: Optional[torch.Tensor] = None,
 ) -> WalkFrame:
     """Second-order biased random walks; same contract as the reference (fugue.py:81-155).
 
@@ -255,7 +279,10 @@ def random_walk(
     * returns ``[src, walk]`` with ``walk_length + 1`` vertices per walk (:153)
     ``random_seed`` keys the Philox stream (None = fresh entropy).  ``checkpoint_dir`` is
     accepted and unused: the walk matrix lives in HBM, there is no lineage to truncate.
-    Keyword-only extras: ``graph`` reuses a prebuilt DeviceGraph; ``collect_stats``.
+    Keyword-only extras: ``graph`` reuses a prebuilt DeviceGraph; ``collect_stats``; ``out`` is a
+    pinned host int32 matrix ``[>= walkers, walk_length + 1]`` to receive the rows -- the walk then
+    runs in chunks of start vertices whose device->host copies overlap the next chunk's kernel
+    (same rows as one launch), and ``WalkFrame.walks`` is a view of ``out``.
     """
     logging.info("random_walk(): start random walking ...")
     for param in NODE2VEC_PARAMS:
@@ -275,11 +302,11 @@ def random_walk(
         src, dst, weight = _graph_arrays(df_graph)
         graph = DeviceGraph.from_arcs(src, dst, weight)
     start = graph.start_vertices()
+    host = None
     if walk_seed is None:
-        walks, alive, stats = graph.walk(start, num_walks, walk_length, p, q, random_seed, collect_stats)
-        walks = walks[alive] if not bool(alive.all()) else walks
+        walks, host, stats = _walk_rows(graph, start, num_walks, walk_length, p, q, random_seed, collect_stats, out)
     else:
-        walks, stats = _walk_from_seed_ids(graph, start, walk_seed, num_walks, walk_length, p, q, random_seed,
-                                           collect_stats)
+        walks, host, stats = _walk_from_seed_ids(graph, start, walk_seed, num_walks, walk_length, p, q, random_seed,
+                                                 collect_stats, out)
     logging.info("random_walk(): random walking done ...")
-    return WalkFrame(walks, stats=stats)
+    return WalkFrame(walks, walks_host=host, stats=stats)

@@ -75,7 +75,7 @@ class DeviceGraph:
                 raise ValueError("src, dst and weight must have the same length")
             n_arcs = int(s.numel())
             if n_vertices is None:
-                n_vertices = int(max(int(s.max()), int(d.max())) + 1) if n_arcs else 0
+                n_vertices = int(torch.maximum(s.max(), d.max())) + 1 if n_arcs else 0      # one host round trip
             g.n_vertices, g.n_arcs = int(n_vertices), n_arcs
             stream = _lib.current_stream_ptr()
             g.vtx = torch.empty((g.n_vertices, 4), dtype=torch.int32, device=device)
@@ -206,6 +206,55 @@ class DeviceGraph:
             if collect_stats:
                 st = dict(zip(_lib.WALK_STAT_NAMES, stats.cpu().tolist()))
         return out[:, : walk_length + 1], alive.bool(), st
+
+
+def walk_to_host(graph, start, num_walks: int, walk_length: int, return_param: float, inout_param: float,
+                 seed: Optional[int], out_host: torch.Tensor, chunk_walkers: int = 1 << 17):
+    """Walk and deliver the rows into a PINNED host matrix, with the device->host copy of chunk k
+    overlapped with the walk kernel of chunk k+1 (two streams).  Chunks are ranges of start vertices;
+    a walker's random stream depends on (seed, start vertex, walk number) only, so the rows are
+    the ones a single launch would give.  ``graph`` is a DeviceGraph or PartitionedGraph.
+    out_host: int32 [>= W, walk_length+1], contiguous, pinned.
+    Returns (walks_device [W, L+1] view, alive_device bool[W]); the call returns with the copy DONE
+    (it synchronises the side stream), rows of dropped walkers are still in place (filter with alive)."""
+    dev = graph.device
+    start_t = _as_device_i32(start, dev)
+    n_start, L1 = int(start_t.numel()), int(walk_length) + 1
+    W, pitch = n_start * int(num_walks), (L1 + 7) // 8 * 8
+    if (out_host.dtype != torch.int32 or out_host.dim() != 2 or out_host.shape[0] < W or out_host.shape[1] != L1
+            or not out_host.is_contiguous() or out_host.device.type != "cpu"):
+        raise ValueError(f"out must be a contiguous int32 host tensor of shape [>= {W}, {L1}]")
+    if not out_host.is_pinned():
+        raise ValueError("out must be pinned host memory (tensor.pin_memory()): the copy is asynchronous")
+    if seed is None:
+        seed = int.from_bytes(os.urandom(8), "little")
+    with torch.cuda.device(dev):
+        # every buffer is allocated on the launching stream and outlives the side stream's work (the call
+        # ends with side.synchronize()), so the caching allocator never sees a cross-stream tensor
+        buf = torch.empty((W, pitch), dtype=torch.int32, device=dev)       # kernel output, pitch-padded rows
+        rows = torch.empty((W, L1), dtype=torch.int32, device=dev)         # compact rows: D2H source, returned
+        cur = torch.cuda.current_stream(dev)
+        side = getattr(graph, "_copy_stream", None)
+        if side is None:
+            side = graph._copy_stream = torch.cuda.Stream(device=dev)
+        per = max(1, int(chunk_walkers) // max(int(num_walks), 1))
+        alive_parts = []
+        for s0 in range(0, n_start, per):
+            s1 = min(n_start, s0 + per)
+            r0, r1 = s0 * int(num_walks), s1 * int(num_walks)
+            _, a, _ = graph.walk(start_t[s0:s1], num_walks, walk_length, return_param, inout_param, seed, out=buf[r0:r1])
+            alive_parts.append(a)
+            # compaction stays on the launching stream: on the side stream it would queue behind the next
+            # chunk's walk kernel for SM slots and serialise the pipeline (measured: 3.3 ms vs 2.9 ms)
+            rows[r0:r1].copy_(buf[r0:r1, :L1])
+            done = torch.cuda.Event()
+            done.record(cur)
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                out_host[r0:r1].copy_(rows[r0:r1], non_blocking=True)
+        alive = torch.cat(alive_parts) if alive_parts else torch.zeros(0, dtype=torch.bool, device=dev)
+        side.synchronize()
+    return rows, alive
 
 
 def walk_consts(return_param: float, inout_param: float, flags: int, has_ratio: bool = False) -> "_lib.WalkConsts":

@@ -454,6 +454,39 @@ def test_random_walk_facade_reference_graph(n2v):
     assert np.array_equal(a, b) and not np.array_equal(c, d)
 
 
+def test_random_walk_pipelined_host_delivery(n2v):
+    """out= (pinned host matrix): chunked walk with overlapped D2H gives the rows of one launch,
+    also when walkers die at sinks, and WalkFrame.walks is a view of the caller's buffer."""
+    import pandas as pd
+    torch = n2v.torch
+    rng = np.random.default_rng(12)
+    for n_src, n_dst in ((3000, 3000), (1500, 3000)):                    # second graph: ids >= 1500 are sinks
+        src, dst = rng.integers(0, n_src, 20000), rng.integers(0, n_dst, 20000)
+        df = pd.DataFrame({"src": src, "dst": dst, "weight": rng.uniform(0.1, 2.0, 20000)})
+        prm = {"num_walks": 7, "walk_length": 11, "return_param": 0.5, "inout_param": 2.0}
+        want = n2v.fugue.random_walk(None, df, dict(prm), random_seed=4).walks
+        n_start = len(set(src.tolist()))
+        host = torch.empty((n_start * 7, 12), dtype=torch.int32).pin_memory()
+        host.fill_(-7)
+        g = n2v.graph.DeviceGraph.from_arcs(src, dst, df["weight"].to_numpy())
+        from node2vec_b200.graph import walk_to_host
+        wd, alive = walk_to_host(g, g.start_vertices(), 7, 11, 0.5, 2.0, 4, host, chunk_walkers=4096)   # many chunks
+        assert np.array_equal(host.numpy()[alive.cpu().numpy()], want) and np.array_equal(wd[alive].cpu().numpy(), want)
+        host.fill_(-7)
+        res = n2v.fugue.random_walk(None, df, dict(prm), random_seed=4, out=host)
+        assert np.array_equal(res.walks, want) and np.array_equal(res.walks_device.cpu().numpy(), want)
+        assert res.walks.ctypes.data == host.numpy().ctypes.data        # no extra host copy
+        assert len(want) < n_start * 7                                  # some walkers died at sinks
+        seeds = pd.DataFrame({"id": np.arange(0, n_src, 2)})
+        a = n2v.fugue.random_walk(None, df, dict(prm), seeds, random_seed=4, out=host).walks.copy()
+        b = n2v.fugue.random_walk(None, df, dict(prm), seeds, random_seed=4).walks
+        assert np.array_equal(a, b)
+    with pytest.raises(ValueError):
+        n2v.fugue.random_walk(None, df, dict(prm), random_seed=4, out=torch.empty((n_start * 7, 12), dtype=torch.int32))
+    with pytest.raises(ValueError):
+        n2v.fugue.random_walk(None, df, dict(prm), random_seed=4, out=host[:10])
+
+
 def test_plain_c_consumer():
     """examples/c_consumer.c: CSR + hash + alias build and a walk driven from plain C through the C
     ABI only (no Python, no torch in the process); it validates every hop on the host itself."""
