@@ -8,6 +8,7 @@ import os
 
 from . import build as _build
 
+N2V_ABI_VERSION = 5          # include/n2v_b200.h
 N2V_MAX_PARTS = 16
 OK, ERR_INVALID, ERR_CUDA, ERR_SCRATCH, ERR_ZERO_WEIGHT = 0, 1, 2, 3, 4
 SUM_MODE = {"naive": 0, "neumaier": 1}
@@ -99,6 +100,8 @@ def load(build_if_missing: bool = True):
         fn = getattr(lib, name)  # AttributeError here = ABI mismatch, loudly
         fn.restype = res
         fn.argtypes = args
+    if lib.n2v_abi_version() != N2V_ABI_VERSION:
+        raise N2VError(f"{path} speaks ABI {lib.n2v_abi_version()}, this package binds ABI {N2V_ABI_VERSION}: rebuild it")
     _lib = lib
     return lib
 
