@@ -14,7 +14,9 @@
 // sub-sampling; rows are D fp32 held NV float4-per-lane in registers, so one row is one
 // coalesced 512-byte gather per 128 dims, the dot is NV fused multiply-adds per lane plus a
 // five-step butterfly, and the centre's positive row stays in registers across its whole
-// context window.  Row updates are Hogwild: `red.global.add.v4.f32` (no lost updates under
+// context window (read once, its updates summed and reduced once per centre: within the warp
+// this is exactly gensim's sequential order; other warps see the centre row's change a window
+// later, which is ordinary Hogwild staleness).  Row updates are Hogwild: `red.global.add.v4.f32` (no lost updates under
 // tens of thousands of concurrent warps) or plain stores (gensim's own lock-free behaviour).
 // This is a gather/scatter path -- (K+2) rows in, (K+2) rows out per pair -- so no tensor
 // cores; the walk buffer is read once per epoch.
@@ -227,7 +229,13 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
       if (j1 - j0 <= 1) continue;
       const int32_t wi = sent[i];
       float* pos_ptr = A.syn1neg + static_cast<int64_t>(wi) * A.dim;
-      Row<NV> pos = load_row<NV, FULL>(pos_ptr, A.dim, lane);   // stays in registers across the window
+      // the centre's row stays in registers across the window: every pair of this centre sees the
+      // updates of the previous ones (gensim's sequential semantics inside the sentence); the sum of
+      // its updates goes out as ONE reduction after the window instead of one per pair
+      Row<NV> pos = load_row<NV, FULL>(pos_ptr, A.dim, lane);
+      Row<NV> pos_delta;
+#pragma unroll
+      for (int q = 0; q < NV; ++q) pos_delta.v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int j = j0; j < j1; ++j) {
         if (j == i) continue;
         const int32_t wj = sent[j];
@@ -249,8 +257,8 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
           const float g = gradient(exp_table, f, 1.0f, alpha, ok);
           if (TRACE) c_clip += ok ? 0u : 1u;
           axpy<NV>(work, g, pos);
-          if (ATOMIC || ok) update_row<NV, ATOMIC, FULL>(pos_ptr, A.dim, lane, g, in, pos);
           axpy<NV>(pos, g, in);
+          if (ATOMIC) axpy<NV>(pos_delta, g, in);
         }
         // K negatives ~ count^0.75, one 8-byte alias gather each
         for (int d = 0; d < K; ++d) {
@@ -285,6 +293,16 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
         add_row<NV, ATOMIC, FULL>(in_ptr, A.dim, lane, work, in);
         ++c_pairs;
         if (TRACE) ++trace_pos;
+      }
+      // centre row: += sum of its updates (ATOMIC), or the register copy stored back (plain Hogwild)
+      if (ATOMIC) {
+        add_row<NV, true, FULL>(pos_ptr, A.dim, lane, pos_delta, pos);
+      } else {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          const int d = (q * 32 + lane) * 4;
+          if (FULL || d < A.dim) *reinterpret_cast<float4*>(pos_ptr + d) = pos.v[q];
+        }
       }
     }
     __syncwarp();
