@@ -72,31 +72,61 @@ __global__ void thresholds(const int64_t* __restrict__ counts, int64_t n, int64_
 // ---- negative-sampling alias table over all ids ----------------------------------------------
 // Not a reference-parity object (gensim bisects a cumulative table; any exact alias table of
 // count^0.75 gives the same law), so it is built for speed: ids are split into "small"
-// (scaled prob < 1) and "large" lists in parallel, their probabilities are packed next to them,
+// (scaled prob < 1) and "large" lists, their probabilities are packed next to them,
 // and ONE thread runs Vose's two-queue merge over the two packed streams.  The merge is
 // sequential but its loads are contiguous and independent of the arithmetic (a few ns per id,
 // ~1 s for 67 M ids) instead of a dependent global-memory round trip per id.
-__global__ void scale_and_split(const double* __restrict__ weight, int64_t n, const double* __restrict__ total,
-                                int32_t* __restrict__ ids, double* __restrict__ packed,
-                                unsigned long long* __restrict__ counters /* [0] smalls, [1] larges */) {
+// Deterministic: ONE CTA walks the ids in order and compacts them with ballot + block scan, so both
+// lists come out in ascending id order and the table (hence every negative drawn from a given
+// random stream) is reproducible run to run.  The level it runs over has at most 262,144 entries
+// (ids beyond 65,536 go through the two-level table), i.e. <= 256 iterations.
+constexpr int kSplitBlock = 1024;
+__global__ void __launch_bounds__(kSplitBlock)
+scale_and_split(const double* __restrict__ weight, int64_t n, const double* __restrict__ total,
+                int32_t* __restrict__ ids, double* __restrict__ packed,
+                unsigned long long* __restrict__ counters /* [0] smalls, [1] larges */) {
+  __shared__ unsigned int w_small[32], w_large[32];
+  __shared__ unsigned int tot_small, tot_large;
+  if (blockIdx.x != 0) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double scale = static_cast<double>(n) / *total;
-  for (int64_t v = blockIdx.x * int64_t(kBlock) + threadIdx.x; v < n; v += int64_t(gridDim.x) * kBlock) {
-    const double p = weight[v] * scale;
-    const bool small = p < 1.0;
-    // warp-aggregated append: smalls grow from the front, larges from the back
-    const unsigned int active = __activemask();
-    const unsigned int m_small = __ballot_sync(active, small);
-    const unsigned int mine = small ? m_small : (active & ~m_small);
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(mine) - 1;
-    unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(counters + (small ? 0 : 1), static_cast<unsigned long long>(__popc(mine)));
-    base = __shfl_sync(active, base, leader);
-    const unsigned long long pos = base + __popc(mine & ((1u << lane) - 1u));
-    const int64_t slot = small ? static_cast<int64_t>(pos) : n - 1 - static_cast<int64_t>(pos);
-    ids[slot] = static_cast<int32_t>(v);
-    packed[slot] = p;
+  unsigned long long base_small = 0, base_large = 0;   // same value in every thread
+  for (int64_t v0 = 0; v0 < n; v0 += kSplitBlock) {
+    const int64_t v = v0 + tid;
+    const bool valid = v < n;
+    const double p = valid ? weight[v] * scale : 0.0;
+    const bool small = valid && p < 1.0;
+    const bool large = valid && !small;
+    const unsigned int m_small = __ballot_sync(0xffffffffu, small);
+    const unsigned int m_large = __ballot_sync(0xffffffffu, large);
+    if (lane == 0) { w_small[warp] = __popc(m_small); w_large[warp] = __popc(m_large); }
+    __syncthreads();
+    if (warp == 0) {   // exclusive scan of the 32 per-warp counts
+      const unsigned int cs = w_small[lane], cl = w_large[lane];
+      unsigned int is = cs, il = cl;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int ts = __shfl_up_sync(0xffffffffu, is, o), tl = __shfl_up_sync(0xffffffffu, il, o);
+        if (lane >= o) { is += ts; il += tl; }
+      }
+      w_small[lane] = is - cs;
+      w_large[lane] = il - cl;
+      if (lane == 31) { tot_small = is; tot_large = il; }
+    }
+    __syncthreads();
+    if (valid) {
+      const unsigned int below = (1u << lane) - 1u;
+      // smalls grow from the front, larges from the back (vose_merge reads them as ids[n-1-j])
+      const int64_t slot = small ? static_cast<int64_t>(base_small + w_small[warp] + __popc(m_small & below))
+                                 : n - 1 - static_cast<int64_t>(base_large + w_large[warp] + __popc(m_large & below));
+      ids[slot] = static_cast<int32_t>(v);
+      packed[slot] = p;
+    }
+    base_small += tot_small;
+    base_large += tot_large;
+    __syncthreads();   // the scan arrays are rewritten by the next iteration
   }
+  if (tid == 0) { counters[0] = base_small; counters[1] = base_large; }
 }
 
 __device__ __forceinline__ uint32_t neg_thr(double p) {
@@ -322,7 +352,7 @@ extern "C" int n2v_sgns_prepare(const int64_t* counts, int64_t n_vertices, int64
   double* d_total = reinterpret_cast<double*>(d_tot + 2);
   N2V_CUDA(cudaMemcpyAsync(d_total, partial, sizeof(double), cudaMemcpyDeviceToDevice, stream));
   N2V_CUDA(cudaMemsetAsync(d_tot, 0, 2 * sizeof(unsigned long long), stream));   // reuse as the two list counters
-  scale_and_split<<<grid_for(level_n), kBlock, 0, stream>>>(level_w, level_n, d_total, ids, packed, d_tot);
+  scale_and_split<<<1, kSplitBlock, 0, stream>>>(level_w, level_n, d_total, ids, packed, d_tot);
   N2V_LAUNCH_OK();
   vose_merge<<<1, 32, 0, stream>>>(ids, packed, level_n, d_tot, level_table);
   N2V_LAUNCH_OK();

@@ -17,7 +17,7 @@ raise NotImplementedError.
 import ctypes as C
 import os
 import pickle
-from typing import Any, Dict, Optional
+from typing import Any, Dict, Optional, Tuple
 
 import numpy as np
 import torch
@@ -229,8 +229,12 @@ class Word2Vec(object):
         self._sync_vectors()
 
     # ------------------------------------------------------------------ training (K3)
-    def train(self, sentences, epochs: Optional[int] = None, trace_cap: int = 0, **ignored):
-        """Run ``epochs`` (default ``iter``) epochs.  Returns (pairs trained, tokens kept)."""
+    def train(self, sentences, epochs: Optional[int] = None, trace_cap: int = 0,
+              epoch_range: Optional[Tuple[int, int]] = None, **ignored):
+        """Run ``epochs`` (default ``iter``) epochs.  Returns (pairs trained, tokens kept).
+        ``epoch_range=(a, b)`` runs only epochs a..b-1 of that ``epochs``-long schedule (learning-rate
+        decay and random streams are functions of the epoch index), so training can be checkpointed
+        with ``save`` between epochs and resumed after ``load`` with the remaining range."""
         lib = _lib.load()
         if self.syn0 is None:
             raise RuntimeError("you must first build vocabulary before training the model")
@@ -247,7 +251,10 @@ class Word2Vec(object):
                                 epoch=0, batch_words=self.batch_words, atomic_updates=int(self.atomic_updates),
                                 alpha=self.alpha, min_alpha=self.min_alpha, seed=self.seed & 0xFFFFFFFFFFFFFFFF,
                                 walk_offset=self._walk_offset, total_walks=self._total_walks)
-            for ep in range(epochs):
+            first, last = (0, epochs) if epoch_range is None else (int(epoch_range[0]), int(epoch_range[1]))
+            if not 0 <= first <= last <= epochs:
+                raise ValueError(f"epoch_range {epoch_range} must lie inside [0, {epochs}]")
+            for ep in range(first, last):
                 P.epoch = ep
                 _lib.check(lib.n2v_sgns_train(_lib.ptr(walks), walks.shape[0], walks.shape[1], walks.stride(0),
                                               _lib.ptr(self._keep), _lib.ptr(self._neg), self._n_rows,
@@ -284,6 +291,10 @@ class Word2Vec(object):
         state["syn0"] = None if self.syn0 is None else self.syn0.cpu().numpy()
         state["syn1neg"] = None if self.syn1neg is None else self.syn1neg.cpu().numpy()
         state["_row_of_index"] = None if self.syn0 is None else self._row_of_index.cpu().numpy()
+        # sampling tables too, so that a loaded model can continue training (train(epoch_range=...))
+        for name in ("_keep", "_neg", "_exp"):
+            t = getattr(self, name, None)
+            state[name] = None if t is None else t.cpu().numpy()
         with open(fname, "wb") as f:
             pickle.dump(state, f, protocol=4)
 
@@ -299,4 +310,7 @@ class Word2Vec(object):
             self.syn0 = torch.as_tensor(state["syn0"], device=dev)
             self.syn1neg = torch.as_tensor(state["syn1neg"], device=dev)
             self._row_of_index = torch.as_tensor(state["_row_of_index"], device=dev)
+            for name in ("_keep", "_neg", "_exp"):
+                if state.get(name) is not None:
+                    setattr(self, name, torch.as_tensor(state[name], device=dev))
         return self

@@ -278,3 +278,38 @@ def test_link_prediction_auc_matches_gensim_restatement(env):
     # plain (non-atomic) Hogwild stores lose updates under ~10^4 concurrent warps on a 1.5k-row
     # table: reported, not gated -- red.global.add is the production path (DESIGN.md "SGNS").
     assert np.mean(auc_plain) > 0.5
+
+
+def test_epoch_range_resumes_the_schedule(env, tmp_path):
+    """train(epochs=4) == train(epoch_range=(0, 2)) + save/load + train(epoch_range=(2, 4)), bit for
+    bit in the deterministic single-warp trace mode: the schedule and the random streams depend on
+    the epoch index only."""
+    torch = env.torch
+    rng = np.random.default_rng(3)
+    walks = torch.as_tensor(rng.integers(0, 60, (40, 12)).astype(np.int32)).cuda()
+
+    def fresh():
+        m = env.sgns.Word2Vec(size=32, window=3, min_count=1, sg=1, negative=3, iter=4, seed=11, sample=0.0)
+        m.build_vocab(walks)
+        return m
+    a = fresh()
+    a.train(walks, epochs=4, trace_cap=8)
+    again = fresh()                                       # everything is reproducible run to run:
+    assert torch.equal(again._neg, a._neg) and torch.equal(again._keep, a._keep)   # the sampling tables
+    again.train(walks, epochs=4, trace_cap=8)
+    assert torch.equal(again.syn0, a.syn0) and torch.equal(again.syn1neg, a.syn1neg)   # and the single-warp fit
+    big = env.sgns.Word2Vec(size=8, min_count=1, sg=1, negative=5, seed=1)
+    big2 = env.sgns.Word2Vec(size=8, min_count=1, sg=1, negative=5, seed=1)
+    wide = torch.as_tensor(rng.integers(0, 100000, (3000, 30)).astype(np.int32)).cuda()   # two-level negative table
+    big.build_vocab(wide)
+    big2.build_vocab(wide)
+    assert torch.equal(big._neg, big2._neg)
+    b = fresh()
+    b.train(walks, epochs=4, trace_cap=8, epoch_range=(0, 2))
+    b.save(str(tmp_path / "half.model"))
+    c = env.sgns.Word2Vec.load(str(tmp_path / "half.model"))
+    c.train(walks, epochs=4, trace_cap=8, epoch_range=(2, 4))
+    assert torch.equal(a.syn0, c.syn0) and torch.equal(a.syn1neg, c.syn1neg)
+    assert not torch.equal(a.syn0, b.syn0)
+    with pytest.raises(ValueError):
+        c.train(walks, epochs=4, epoch_range=(3, 5))
