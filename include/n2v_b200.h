@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define N2V_ABI_VERSION 5
+#define N2V_ABI_VERSION 6
 #define N2V_MAX_PARTS 16
 
 /* error codes */
@@ -240,6 +240,19 @@ int n2v_walk_consts(double return_param, double inout_param, uint32_t graph_flag
  * returning through the fold, e*rev / (1 + e*rev), needs one 8-byte gather per step and no
  * search.  Single-part graphs; ratio_out: [n_arcs][2] fp32.  Run after n2v_alias_build. */
 int n2v_ratio_build(const n2v_graph_t* graph, float* ratio_out, void* stream);
+
+/* ---- K5: hotspot trimming, bit-exact with the reference's sampler ------------------------
+ * Replaces trim_hotspot_vertices (randomwalk.py:238-262): a vertex with more than `cap` out-arcs
+ * keeps `DataFrame.sample(n=cap, random_state=seed)` of them, i.e. numpy's legacy
+ * RandomState(seed).permutation(deg)[:cap] (Fisher-Yates from the top index down, swap partners by
+ * masked rejection from 32-bit MT19937 outputs; every partition re-seeds, so the kept positions
+ * depend on (seed, deg) only).
+ * deg[n_hot]: out-degrees of the hot vertices (each > cap is the intended use; any deg >= 1 works);
+ * scratch_offset[n_hot]: start of vertex h's slice in scratch (exclusive prefix sum of deg);
+ * scratch: int32[sum(deg)];  picked[n_hot][cap]: picked[h][k] = position (0-based, in the vertex's
+ * input order) of the k-th kept arc, in the order pandas returns them.  Asynchronous. */
+int n2v_trim_sample(const int64_t* deg, const int64_t* scratch_offset, int64_t n_hot, int32_t cap,
+                    uint32_t seed, int32_t* scratch, int32_t* picked, void* stream);
 
 
 /* ---- peer-shareable device buffers (vertex-partitioned CSR over NVLink) ----------------

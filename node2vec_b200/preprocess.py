@@ -2,16 +2,20 @@
 ``trim_index`` (reference fugue.py:24-77) that precedes the hot path -- hotspot trimming
 (randomwalk.py:238-262) and the undirected expansion of the indexer (indexer.py:45-48).
 
-Data-preparation built from torch primitives (sort / unique / bincount on the GPU); not
-part of the measured hot path.  The pandas path in ``fugue.trim_index`` stays the bit-exact
-twin of the reference (same numpy RandomState sampling); here the sample is drawn with a
-seeded torch generator -- the same law (uniform without replacement, ``max_out_deg`` arcs per
-oversize vertex), not the same bits.
+Data-preparation built from torch primitives (sort / unique / bincount on the GPU) plus K5
+``n2v_trim_sample``; not part of the measured hot path.  With a ``seed`` the kept arcs and their
+order are bit-identical to the reference's pandas path (``DataFrame.sample(n, random_state=seed)``
+= numpy's legacy ``RandomState(seed).permutation(deg)[:n]``, re-seeded per vertex; the kernel runs
+MT19937 and the Fisher-Yates shuffle on the device).  Without a seed the reference draws from the
+unseeded global generator; here a torch generator draws the same law (uniform without
+replacement).
 """
+import ctypes as C
 from typing import Optional, Tuple
 
 import torch
 
+from . import _lib
 from .constants import MAX_OUT_DEGREES
 
 
@@ -25,11 +29,10 @@ def trim_hotspots_device(src: torch.Tensor, dst: torch.Tensor, weight: Optional[
     deg = torch.bincount(s, minlength=n)
     if s.numel() == 0 or int(deg.max()) <= cap:
         return src, dst, weight
-    gen = torch.Generator(device=src.device)
     if seed is not None:
-        gen.manual_seed(int(seed))
-    else:
-        gen.seed()
+        return _trim_exact(src, dst, weight, s, deg, cap, int(seed))
+    gen = torch.Generator(device=src.device)
+    gen.seed()
     over = deg[s] > cap                                   # arcs of oversize vertices
     idx = torch.nonzero(over).view(-1)
     key = (s[idx] << 31) | torch.randint(0, 2 ** 31 - 1, (idx.numel(),), device=src.device, generator=gen)
@@ -42,6 +45,38 @@ def trim_hotspots_device(src: torch.Tensor, dst: torch.Tensor, weight: Optional[
     keep = torch.ones(src.numel(), dtype=torch.bool, device=src.device)
     keep[idx[order[rank >= cap]]] = False
     return src[keep], dst[keep], (None if weight is None else weight[keep])
+
+
+def _trim_exact(src, dst, weight, s, deg, cap: int, seed: int):
+    """The reference's output, row for row: partitions in ascending ``src`` order (fugue.py:57-67),
+    untouched partitions in input order, an oversize partition replaced by its rows at positions
+    ``RandomState(seed).permutation(deg)[:cap]`` in that order (randomwalk.py:256-260)."""
+    if not 0 <= seed <= 0xFFFFFFFF:
+        raise ValueError("Seed must be between 0 and 2**32 - 1")          # numpy's own message
+    dev = src.device
+    n = int(deg.numel())
+    order = torch.argsort(s, stable=True)                                 # ascending src, input order inside
+    group_start = torch.cumsum(deg, 0) - deg
+    hot = torch.nonzero(deg > cap).view(-1)
+    n_hot = int(hot.numel())
+    hot_deg = deg[hot].contiguous()
+    scratch_off = (torch.cumsum(hot_deg, 0) - hot_deg).contiguous()
+    scratch = torch.empty(int(hot_deg.sum()), dtype=torch.int32, device=dev)
+    picked = torch.empty((n_hot, cap), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().n2v_trim_sample(_lib.ptr(hot_deg), _lib.ptr(scratch_off), n_hot, cap, C.c_uint32(seed),
+                                               _lib.ptr(scratch), _lib.ptr(picked), _lib.current_stream_ptr()),
+                   "n2v_trim_sample")
+    new_deg = deg.clamp(max=cap)
+    out_start = torch.cumsum(new_deg, 0) - new_deg
+    v = torch.repeat_interleave(torch.arange(n, device=dev), new_deg)     # vertex of every output row
+    r = torch.arange(int(v.numel()), device=dev) - out_start[v]           # its rank inside the vertex
+    hot_index = torch.full((n,), -1, dtype=torch.int64, device=dev)
+    hot_index[hot] = torch.arange(n_hot, device=dev)
+    hi = hot_index[v]
+    pos = torch.where(hi >= 0, picked[hi.clamp(min=0), r.clamp(max=cap - 1)].to(torch.int64), r)
+    sel = order[group_start[v] + pos]
+    return src[sel], dst[sel], (None if weight is None else weight[sel])
 
 
 def symmetrise_device(src: torch.Tensor, dst: torch.Tensor, weight: Optional[torch.Tensor] = None

@@ -80,3 +80,58 @@ def trim_hotspot(
     if not parts:
         return df
     return pd.concat(parts, ignore_index=True)
+
+
+# ----------------------------------------------------------------------------------
+# numpy's legacy RandomState(seed).permutation(n), restated (what K5 n2v_trim_sample runs)
+# ----------------------------------------------------------------------------------
+class _MT19937(object):
+    """MT19937 as numpy seeds it for an int seed (mt19937_seed == init_genrand) and draws 32-bit
+    words from it (mt19937_next)."""
+
+    def __init__(self, seed: int):
+        if not 0 <= seed <= 0xFFFFFFFF:
+            raise ValueError("Seed must be between 0 and 2**32 - 1")
+        self.key = [0] * 624
+        for pos in range(624):
+            self.key[pos] = seed
+            seed = (1812433253 * (seed ^ (seed >> 30)) + pos + 1) & 0xFFFFFFFF
+        self.pos = 624
+
+    def _refill(self):
+        k = self.key
+        for i in range(624):
+            y = (k[i] & 0x80000000) | (k[(i + 1) % 624] & 0x7FFFFFFF)
+            k[i] = k[(i + 397) % 624] ^ (y >> 1) ^ (0x9908B0DF if y & 1 else 0)
+        self.pos = 0
+
+    def next32(self) -> int:
+        if self.pos == 624:
+            self._refill()
+        y = self.key[self.pos]
+        self.pos += 1
+        y ^= y >> 11
+        y ^= (y << 7) & 0x9D2C5680
+        y ^= (y << 15) & 0xEFC60000
+        y ^= y >> 18
+        return y & 0xFFFFFFFF
+
+
+def numpy_legacy_permutation(n: int, seed: int) -> List[int]:
+    """``np.random.RandomState(seed).permutation(n)``: shuffle(arange(n)) = Fisher-Yates from the top
+    index down, the partner of index i drawn by masked rejection (``random_interval(i)``: smallest
+    all-ones mask >= i, draw 32-bit words until ``word & mask <= i``).  pandas' ``DataFrame.sample(
+    n=k, random_state=seed)`` -- the reference's hotspot trimming, randomwalk.py:256-260 -- keeps rows
+    ``permutation(len)[:k]`` in that order."""
+    rng = _MT19937(seed)
+    arr = list(range(n))
+    for i in range(n - 1, 0, -1):
+        mask = i
+        for sh in (1, 2, 4, 8, 16):
+            mask |= mask >> sh
+        while True:
+            j = rng.next32() & mask
+            if j <= i:
+                break
+        arr[i], arr[j] = arr[j], arr[i]
+    return arr

@@ -33,7 +33,7 @@ def test_header_symbols_exported(lib):
 
 def test_abi_version_and_struct_sizes(lib):
     from node2vec_b200 import _lib
-    assert lib.n2v_abi_version() == 5
+    assert lib.n2v_abi_version() == 6
     assert C.sizeof(_lib.GraphPart) == 48
     assert C.sizeof(_lib.Graph) == 8 + 8 + 4 + 4 + 8 + 48 * 16
     assert C.sizeof(_lib.WalkConsts) == 40

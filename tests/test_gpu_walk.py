@@ -495,7 +495,7 @@ def test_plain_c_consumer():
     exe = nb.build_c_consumer()
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr + out.stdout
-    assert out.stdout.startswith("c_consumer OK abi=5") and "dropped_at_sink=" in out.stdout
+    assert out.stdout.startswith("c_consumer OK abi=6") and "dropped_at_sink=" in out.stdout
     fields = dict(kv.split("=") for kv in out.stdout.split()[2:])
     assert int(fields["walkers"]) == 999 * 4 and int(fields["alive"]) + int(fields["dropped_at_sink"]) == 999 * 4
     assert int(fields["dropped_at_sink"]) > 0 and int(fields["alive"]) > 0
@@ -608,6 +608,45 @@ def test_device_trim_and_symmetrise(n2v):
     assert len(s3) == len(e)
     out, none = n2v.fugue.trim_index(None, (ts, td, tw), indexed=True, directed=True, max_out_deg=100, random_seed=3)
     assert none is None and torch.equal(out[1], d2)
+
+
+def test_device_trim_bit_exact_with_reference_sampler(n2v):
+    """K5 n2v_trim_sample: the kept positions are numpy's RandomState(seed).permutation(deg)[:cap]
+    (what pandas' DataFrame.sample evaluates to), and the tensor path of trim_index returns the same
+    rows in the same order as the pandas path, which the reference goldens pin."""
+    import ctypes as C
+    import pandas as pd
+    torch = n2v.torch
+    lib = n2v.lib.load()
+    for seed, cap in ((0, 1), (5, 7), (2 ** 32 - 1, 100)):
+        degs = [cap + 1, 2 * cap + 3, 1000, 1000, 4097, 70001]
+        deg = torch.as_tensor(degs, dtype=torch.int64, device="cuda")
+        off = torch.cumsum(deg, 0) - deg
+        scratch = torch.empty(int(deg.sum()), dtype=torch.int32, device="cuda")
+        picked = torch.full((len(degs), cap), -1, dtype=torch.int32, device="cuda")
+        n2v.lib.check(lib.n2v_trim_sample(n2v.lib.ptr(deg), n2v.lib.ptr(off), len(degs), cap, C.c_uint32(seed),
+                                          n2v.lib.ptr(scratch), n2v.lib.ptr(picked), n2v.lib.current_stream_ptr()))
+        got = picked.cpu().numpy()
+        for h, d in enumerate(degs):
+            assert got[h].tolist() == np.random.RandomState(seed).permutation(d)[:cap].tolist(), (seed, cap, d)
+    # whole trim_index, tensor path vs pandas path (multi-arcs, weights, several hot vertices, untouched ones)
+    rng = np.random.default_rng(8)
+    src = np.concatenate([rng.integers(0, 40, 600), np.full(3000, 11), np.full(900, 3), np.full(901, 25)])
+    perm = rng.permutation(len(src))
+    src = src[perm]
+    dst = rng.integers(0, 5000, len(src))
+    w = rng.uniform(0.1, 2.0, len(src))
+    df = pd.DataFrame({"src": src, "dst": dst, "weight": w})
+    for seed, cap in ((3, 50), (77, 800)):
+        want = n2v.fugue.trim_index(None, df, indexed=True, max_out_deg=cap, random_seed=seed)[0].as_pandas()
+        out, none = n2v.fugue.trim_index(None, tuple(torch.as_tensor(x, device="cuda") for x in (src, dst, w)),
+                                         indexed=True, max_out_deg=cap, random_seed=seed)
+        assert none is None
+        assert out[0].cpu().tolist() == want["src"].tolist() and out[1].cpu().tolist() == want["dst"].tolist()
+        assert out[2].cpu().numpy().tobytes() == want["weight"].to_numpy().tobytes()
+    with pytest.raises(ValueError):
+        n2v.fugue.trim_index(None, (torch.as_tensor(src, device="cuda"), torch.as_tensor(dst, device="cuda")),
+                             indexed=True, max_out_deg=50, random_seed=2 ** 32)
 
 
 def test_full_size_properties_config3(n2v):

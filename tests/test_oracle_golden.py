@@ -235,3 +235,16 @@ def test_verbatim_fugue_trim_index():
             s, d = s.tolist(), d.tolist()
         assert s == c["src"] and d == c["dst"], kw
         assert [float(x).hex() for x in np.asarray(w).tolist()] == c["weight"]
+
+
+def test_numpy_legacy_permutation_restatement():
+    """oracle/ref_indexer.py::numpy_legacy_permutation (the algorithm K5 runs on the device) against
+    numpy itself and against pandas.DataFrame.sample, the call the reference makes."""
+    import pandas as pd
+    for seed in (0, 5, 2 ** 32 - 1):
+        for n in (1, 2, 9, 624, 625, 3000):
+            assert ref_indexer.numpy_legacy_permutation(n, seed) == np.random.RandomState(seed).permutation(n).tolist()
+    df = pd.DataFrame({"x": range(700)})
+    assert df.sample(n=30, random_state=4)["x"].tolist() == ref_indexer.numpy_legacy_permutation(700, 4)[:30]
+    with pytest.raises(ValueError):
+        ref_indexer.numpy_legacy_permutation(5, 2 ** 32)
