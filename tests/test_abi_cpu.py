@@ -209,6 +209,24 @@ def test_trim_index_facade_matches_verbatim_reference():
             assert nid["vertex_name"].tolist() == c["name_id"]["vertex_name"]
 
 
+def test_example_pipeline_index_stage(tmp_path):
+    """examples/pipeline.py, stage 1 (host only): parquet in, indexed graph + name map out."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("n2v_example_pipeline", os.path.join(root, "examples", "pipeline.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    pd.DataFrame({"src": ["a", "a", "b", "c", "a"], "dst": ["b", "c", "c", "a", "b"],
+                  "weight": [1.0, 2.0, 0.5, 1.5, 1.0]}).to_parquet(tmp_path / "input_graph.parquet")
+    mod.stage_index(str(tmp_path))
+    g = pd.read_parquet(tmp_path / "graph_indexed.parquet")
+    nid = pd.read_parquet(tmp_path / "graph_name2id.parquet")
+    assert list(g.columns) == ["src", "dst", "weight"] and len(g) == 4                    # the duplicate row is gone
+    # the reference's ids: position of a name's first occurrence in [src..., dst...] (indexer.py:26-35)
+    assert dict(zip(nid["vertex_name"], nid["vertex_id"])) == {"a": 0, "b": 2, "c": 3}
+    assert sorted(zip(g["src"], g["dst"])) == [(0, 2), (0, 3), (2, 3), (3, 0)]
+
+
 def test_walk_frame_parquet_round_trip(tmp_path):
     """The [src, walk] wire format (host logic only: a WalkFrame over a CPU tensor)."""
     import numpy as np

@@ -313,3 +313,27 @@ def test_epoch_range_resumes_the_schedule(env, tmp_path):
     assert not torch.equal(a.syn0, b.syn0)
     with pytest.raises(ValueError):
         c.train(walks, epochs=4, epoch_range=(3, 5))
+
+
+def test_example_pipeline_end_to_end(env, tmp_path):
+    """examples/pipeline.py: the reference example's three stages, parquet in / parquet out."""
+    import importlib.util
+    import pandas as pd
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("n2v_example_pipeline", os.path.join(root, "examples", "pipeline.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(1)
+    names = np.array([f"user{i}" for i in range(300)])
+    a, b = rng.integers(0, 300, 3000), rng.integers(0, 300, 3000)
+    pd.DataFrame({"src": names[a], "dst": names[b], "weight": rng.uniform(0.5, 2.0, 3000)}).to_parquet(
+        tmp_path / "input_graph.parquet")
+    mod.stage_index(str(tmp_path))
+    mod.stage_walk(str(tmp_path), random_seed=3)
+    mod.stage_embed(str(tmp_path), random_seed=3)
+    walks = pd.read_parquet(tmp_path / "graph_walks.parquet")
+    assert list(walks.columns) == ["src", "walk"] and all(len(w) == 11 for w in walks["walk"][:50])
+    emb = pd.read_parquet(tmp_path / "graph_embedding.parquet")
+    assert list(emb.columns) == ["name", "vector"] and len(emb) > 250 and len(emb["vector"][0]) == 128
+    assert set(emb["name"]) <= set(names)
+    assert os.path.exists(tmp_path / "graph_vectors.txt")
