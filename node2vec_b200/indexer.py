@@ -68,3 +68,10 @@ def index_graph_dense(df_graph: pd.DataFrame, directed: bool) -> Tuple[pd.DataFr
         mirror = pd.DataFrame({"src": df_edge["dst"], "dst": df_edge["src"], "weight": df_edge["weight"]})
         df_edge = pd.concat([df_edge, mirror]).drop_duplicates()
     return df_edge, name_id
+
+
+def index_graph_spark(df_graph, directed: bool):
+    """The reference's Spark indexer (indexer.py:52-85) runs on a SparkSession, which is outside
+    the hot path; ``index_graph_dense`` applies its id rule (dense rank of the sorted names) to a
+    pandas frame."""
+    raise NotImplementedError("index_graph_spark needs Spark (out of scope): use index_graph_dense for the same ids")

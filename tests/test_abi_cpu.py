@@ -185,6 +185,9 @@ def test_indexer_facade_bit_exact():
     assert len(vid) == 6 and len(e) == 8
     with pytest.raises(ValueError):
         index_graph_pandas(pd.DataFrame({"dst": ["a"], "weight": [1.0]}), True)
+    from node2vec_b200.indexer import index_graph_spark
+    with pytest.raises(NotImplementedError):
+        index_graph_spark(g, False)
     e, vid = index_graph_dense(pd.DataFrame({"src": ["b", "a"], "dst": ["c", "b"]}), True)
     assert vid["id"].tolist() == [0, 1, 2] and vid["name"].tolist() == ["a", "b", "c"]
     assert e["src"].tolist() == [1, 0] and e["dst"].tolist() == [2, 1]
