@@ -356,7 +356,34 @@ def bench_sgns(args, torch, dist, dev, world, rank, walks, w, flush, host_walks,
     b_pair = sgns_bytes_per_pair(dim, K)
     kernel_ms = float(np.mean(ms))
     achieved = (pairs / args.steps) * b_pair / (kernel_ms * 1e-3) / 1e9
+    shared = None
+    if world == 1 and dim <= 128 and K == 5:
+        # informational: the opt-in window-shared-negatives kernel (csrc/sgns_shared.cu) on the same matrix.
+        # A different sampling scheme (K negatives drawn once per centre), so it is NOT `value`.
+        try:
+            ms_ = Word2Vec(size=dim, sg=1, iter=4, seed=1, batch_words=10000, share_negatives=True, **SGNS_HP)
+            ms_.build_vocab(walks)
+            ms_.train(walks, epochs=1)
+            torch.cuda.synchronize()
+            t_sh, p_sh = [], 0
+            for _ in range(3):
+                flush.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ms_.train(walks, epochs=1)
+                b.record()
+                torch.cuda.synchronize()
+                t_sh.append(a.elapsed_time(b))
+                p_sh = ms_.train_stats["pairs"]
+            shared = {"value": p_sh / (float(np.mean(t_sh)) * 1e-3), "unit": "pairs/s", "ms_per_step": float(np.mean(t_sh)),
+                      "steps": 3, "note": "opt-in Word2Vec(share_negatives=True): negatives drawn once per centre, "
+                                          "target rows register-resident across the window; AUC within +-0.01 of the "
+                                          "per-pair kernel (tests/test_gpu_sgns_shared.py); not the parity path"}
+            del ms_
+        except Exception as exc:      # never let the experiment disturb the bench line
+            shared = {"unavailable": repr(exc)[:200]}
     return {
+        "shared_negatives": shared,
         "metric": "sgns_pairs_per_s", "value": value, "unit": "pairs/s", "ms_per_step": total_ms / args.steps,
         "dtype": "f32", "gpu_launches": args.steps,
         "config": {"dim": dim, **SGNS_HP, "walks_per_gpu": int(walks.shape[0]), "tokens_per_walk": int(walks.shape[1]),

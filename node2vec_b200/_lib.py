@@ -72,6 +72,8 @@ _SIGNATURES = {
     "n2v_sgns_exp_table": (C.c_int, [C.POINTER(C.c_float)]),
     "n2v_sgns_train": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, _P, _P, C.c_int64, _P, _P, _P,
                                  C.POINTER(SgnsParams), _P, _P, _P, C.c_int64, _P]),
+    "n2v_sgns_train_shared": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, _P, _P, C.c_int64, _P, _P, _P,
+                                        C.POINTER(SgnsParams), _P, _P, _P, C.c_int64, _P]),
     "n2v_scale": (C.c_int, [_P, C.c_int64, C.c_float, _P]),
 }
 

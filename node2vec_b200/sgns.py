@@ -147,7 +147,8 @@ def _walk_matrix(sentences, device) -> torch.Tensor:
 class Word2Vec(object):
     def __init__(self, sentences=None, size=100, alpha=0.025, window=5, min_count=5, sample=1e-3, seed=1,
                  workers=3, min_alpha=0.0001, sg=0, hs=0, negative=5, ns_exponent=0.75, iter=5,
-                 batch_words=10000, atomic_updates=True, process_group=None, sync_every=1, **ignored):
+                 batch_words=10000, atomic_updates=True, process_group=None, sync_every=1,
+                 share_negatives=False, **ignored):
         _lib.require_cuda()
         if hs:
             raise NotImplementedError("hierarchical softmax (hs=1) is outside the SGNS hot path")
@@ -161,6 +162,11 @@ class Word2Vec(object):
         self.epochs = self.iter = int(iter)
         self.batch_words = int(batch_words)
         self.atomic_updates = bool(atomic_updates)
+        # EXPERIMENTAL, off by default: draw the K negatives once per centre instead of once per pair
+        # (csrc/sgns_shared.cu); a different sampling scheme with its own AUC gate, not the parity path
+        self.share_negatives = bool(share_negatives)
+        if self.share_negatives and (size > 128 or negative != 5 or not atomic_updates):
+            raise ValueError("share_negatives needs size <= 128, negative == 5 and atomic_updates=True")
         self.process_group, self.sync_every = process_group, max(1, int(sync_every))
         self.wv = KeyedVectors(self.vector_size)
         self.corpus_count = 0
@@ -256,11 +262,12 @@ class Word2Vec(object):
                 raise ValueError(f"epoch_range {epoch_range} must lie inside [0, {epochs}]")
             for ep in range(first, last):
                 P.epoch = ep
-                _lib.check(lib.n2v_sgns_train(_lib.ptr(walks), walks.shape[0], walks.shape[1], walks.stride(0),
-                                              _lib.ptr(self._keep), _lib.ptr(self._neg), self._n_rows,
-                                              _lib.ptr(self.syn0), _lib.ptr(self.syn1neg), _lib.ptr(self._exp),
-                                              C.byref(P), _lib.ptr(stats), _lib.ptr(trace), _lib.ptr(trace_alpha),
-                                              trace_cap, _lib.current_stream_ptr()), "n2v_sgns_train")
+                entry = lib.n2v_sgns_train_shared if getattr(self, "share_negatives", False) else lib.n2v_sgns_train
+                _lib.check(entry(_lib.ptr(walks), walks.shape[0], walks.shape[1], walks.stride(0),
+                                 _lib.ptr(self._keep), _lib.ptr(self._neg), self._n_rows,
+                                 _lib.ptr(self.syn0), _lib.ptr(self.syn1neg), _lib.ptr(self._exp),
+                                 C.byref(P), _lib.ptr(stats), _lib.ptr(trace), _lib.ptr(trace_alpha),
+                                 trace_cap, _lib.current_stream_ptr()), "n2v_sgns_train")
                 if self.process_group is not None and ((ep + 1) % self.sync_every == 0 or ep + 1 == epochs):
                     self.average_tables()
         st = dict(zip(_lib.SGNS_STAT_NAMES, stats.cpu().tolist()))
