@@ -361,7 +361,8 @@ def gen_fugue_verbatim(rng):
     return {"native_sum_mode": native_mode_name(), "walks": walks, "trim_index": trims}
 
 
-def main():
+def main(out_dir=None):
+    out_dir = out_dir or HERE
     rng = random.Random(20261017)
     files = {
         "alias_tables.json": gen_alias(rng),
@@ -376,10 +377,10 @@ def main():
             "reference": "graph-embedding/node2vec 0.3.5 (node2vec-fugue), imported from " + REF}
     for name, payload in files.items():
         payload["_meta"] = meta
-        with open(os.path.join(HERE, name), "w") as f:
+        with open(os.path.join(out_dir, name), "w") as f:
             json.dump(payload, f, separators=(",", ":"))
-        print(name, os.path.getsize(os.path.join(HERE, name)), "bytes")
+        print(name, os.path.getsize(os.path.join(out_dir, name)), "bytes")
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

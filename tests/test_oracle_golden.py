@@ -5,6 +5,7 @@ Fixtures under tests/golden/ were produced by running the unmodified reference
 through their hex strings.  Also restates the known-answer vectors of the
 reference's own tests/test_randomwalk.py.
 """
+import os
 import random
 
 import numpy as np
@@ -248,3 +249,21 @@ def test_numpy_legacy_permutation_restatement():
     assert df.sample(n=30, random_state=4)["x"].tolist() == ref_indexer.numpy_legacy_permutation(700, 4)[:30]
     with pytest.raises(ValueError):
         ref_indexer.numpy_legacy_permutation(5, 2 ** 32)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("N2V_REFERENCE", "/root/reference")),
+                    reason="the reference checkout only exists in the build container")
+def test_fixtures_regenerate_from_the_unmodified_reference(tmp_path):
+    """Re-run tests/golden/make_golden.py against the live reference checkout (a fresh interpreter:
+    the script stubs pyspark / shims DataFrame.append) and require byte-identical fixtures: the
+    committed goldens are what the unmodified reference computes, today."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run([sys.executable, os.path.join(root, "tests", "golden", "make_golden.py"), str(tmp_path)],
+                   check=True, capture_output=True, timeout=600, env={**os.environ, "PYTHONDONTWRITEBYTECODE": "1"})
+    names = sorted(f for f in os.listdir(tmp_path) if f.endswith(".json"))
+    assert names == sorted(f for f in os.listdir(os.path.join(root, "tests", "golden")) if f.endswith(".json"))
+    for name in names:
+        with open(os.path.join(tmp_path, name), "rb") as a, open(os.path.join(root, "tests", "golden", name), "rb") as b:
+            assert a.read() == b.read(), name
