@@ -7,7 +7,7 @@ walk shards with replicated tables: token counts are sum-reduced once, the two e
 are averaged (sum-allreduce over NVLink, then x 1/G) at a fixed interval.
 Everything here is backend-agnostic so the bookkeeping is tested with gloo on CPU.
 """
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 

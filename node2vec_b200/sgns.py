@@ -15,9 +15,8 @@ gensim 3.8 (the reference's own defaults, constants.py:50-68).  CBOW / hierarchi
 raise NotImplementedError.
 """
 import ctypes as C
-import os
 import pickle
-from typing import Any, Dict, Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch

@@ -6,7 +6,6 @@ import torch
 import bench
 from node2vec_b200.graph import DeviceGraph
 from node2vec_b200.sgns import Word2Vec
-from node2vec_b200 import _lib
 
 name = sys.argv[1] if len(sys.argv) > 1 else "blogcatalog_like"
 w = bench.WORKLOADS[name]
