@@ -230,6 +230,33 @@ def test_example_pipeline_index_stage(tmp_path):
     assert sorted(zip(g["src"], g["dst"])) == [(0, 2), (0, 3), (2, 3), (3, 0)]
 
 
+def test_keyed_vectors_word2vec_text_format(tmp_path):
+    """The embedding wire format (embedding.py:166-178 -> wv.save_word2vec_format / load_word2vec_format):
+    header "<n> <dim>", one "<token> <floats>" line per vertex, most frequent first; fp32 survives the text
+    round trip bit for bit (shortest-repr floats); loaded counts follow gensim's n - i convention."""
+    import numpy as np
+    from node2vec_b200.sgns import KeyedVectors, Vocab
+    rng = np.random.default_rng(0)
+    kv = KeyedVectors(6)
+    kv.vectors = rng.standard_normal((4, 6)).astype(np.float32) * np.float32(1e-3)
+    kv.index2word = ["17", "3", "250", "8"]
+    kv.vocab = {w: Vocab(count=100 - 10 * i, index=i) for i, w in enumerate(kv.index2word)}
+    path = str(tmp_path / "vectors.txt")
+    kv.save_word2vec_format(path)
+    lines = open(path).read().splitlines()
+    assert lines[0] == "4 6" and [ln.split(" ")[0] for ln in lines[1:]] == kv.index2word
+    assert all(len(ln.split(" ")) == 7 for ln in lines[1:])
+    back = KeyedVectors.load_word2vec_format(path)
+    assert back.index2word == kv.index2word and back.vector_size == 6 and len(back) == 4
+    assert back.vectors.dtype == np.float32 and np.array_equal(back.vectors, kv.vectors)
+    assert [back.vocab[w].count for w in back.index2word] == [4, 3, 2, 1]
+    assert np.array_equal(back["250"], kv.vectors[2]) and np.array_equal(back[250], kv.vectors[2])
+    assert np.array_equal(back[["3", "8"]], kv.vectors[[1, 3]])
+    assert "17" in back and 17 in back and "18" not in back
+    with pytest.raises(KeyError):
+        back["18"]
+
+
 def test_walk_frame_parquet_round_trip(tmp_path):
     """The [src, walk] wire format (host logic only: a WalkFrame over a CPU tensor)."""
     import numpy as np
