@@ -230,6 +230,39 @@ def test_example_pipeline_index_stage(tmp_path):
     assert sorted(zip(g["src"], g["dst"])) == [(0, 2), (0, 3), (2, 3), (3, 0)]
 
 
+def test_reference_test_trim_index_against_facade_with_fugue_like_frames():
+    """The engine-independent half of the reference's tests/test_fugue.py::test_trim_index (:13-56), run
+    against THIS package with Fugue-shaped inputs (the pandas stand-in for Fugue's ArrayDataFrame /
+    PandasDataFrame / NativeExecutionEngine under tests/golden/fugue_shim): same calls, same assertions."""
+    import sys
+    shim = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fugue_shim")
+    sys.path.insert(0, shim)
+    try:
+        from fugue import ArrayDataFrame, NativeExecutionEngine, PandasDataFrame
+    finally:
+        sys.path.remove(shim)
+    from node2vec_b200.fugue import trim_index
+
+    graph = [[0, 2, 0.41], [0, 4, 0.85], [3, 4, 0.36], [2, 0, 0.68], [4, 0, 0.1], [4, 3, 0.37]]
+    df = ArrayDataFrame(graph, schema="src:int,dst:int,weight:double")
+    df_res, name_id = trim_index(NativeExecutionEngine(), df, indexed=True)
+    assert len(df_res.as_pandas()) == 6 and name_id is None
+    df_res, name_id = trim_index(NativeExecutionEngine(), df, indexed=True, max_out_deg=1)
+    assert len(df_res.as_pandas()) == 4 and name_id is None
+    dat1 = {"src": ["a1", "a1", "a1", "a2", "b2"], "dst": ["a2", "b1", "b2", "b1", "a2"]}
+    dat2 = {"dst": ["a2", "b1", "b2", "a1"], "weight": [0.8, 1.1, 1.0, 0.3]}
+    df_res, name_id = trim_index(NativeExecutionEngine(), PandasDataFrame(pd.DataFrame.from_dict(dat1)), indexed=False)
+    assert len(df_res.as_pandas()) == 5 and len(name_id.as_pandas()) == 4
+    df_res, name_id = trim_index(NativeExecutionEngine(), PandasDataFrame(pd.DataFrame.from_dict(dat1)),
+                                 indexed=False, max_out_deg=2)
+    assert df_res.count() == 4 and name_id.count() == 4                 # the Spark half's numbers (:35-38)
+    pytest.raises(ValueError, trim_index, NativeExecutionEngine(), PandasDataFrame(pd.DataFrame.from_dict(dat2)), False)
+
+    class SparkExecutionEngine:                                          # Spark engines are refused, loudly
+        pass
+    pytest.raises(NotImplementedError, trim_index, SparkExecutionEngine(), df, True)
+
+
 def test_keyed_vectors_word2vec_text_format(tmp_path):
     """The embedding wire format (embedding.py:166-178 -> wv.save_word2vec_format / load_word2vec_format):
     header "<n> <dim>", one "<token> <floats>" line per vertex, most frequent first; fp32 survives the text
