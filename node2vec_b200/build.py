@@ -41,10 +41,27 @@ def build_library(force: bool = False, extra_flags=(), verbose: bool = False) ->
     nvcc = _nvcc()
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libn2v_b200.so")
-    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-o", SO] + sources()
-    if verbose:
-        print(" ".join(cmd), file=sys.stderr)
-    subprocess.check_call(cmd, cwd=CSRC)
+    # one builder at a time (torchrun starts one process per GPU; all of them may find the .so stale):
+    # an exclusive file lock, the build goes to a temporary name and is renamed into place, so no
+    # process can ever dlopen a half-written library
+    import fcntl
+    with open(SO + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():          # somebody else built it while we waited
+                return SO
+            tmp = f"{SO}.{os.getpid()}.tmp"
+            cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-o", tmp] + sources()
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            try:
+                subprocess.check_call(cmd, cwd=CSRC)
+                os.replace(tmp, SO)
+            finally:
+                if os.path.exists(tmp):
+                    os.unlink(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO
 
 

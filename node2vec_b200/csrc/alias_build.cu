@@ -27,16 +27,65 @@ __device__ __forceinline__ uint32_t prob_to_thr(double pr) {
   return s >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(s);
 }
 
+// the sequential per-vertex construction on ONE thread (global-memory work lists)
+__device__ void build_vertex_sequential(n2v_vertex_t* __restrict__ vtx, const n2v_vertex_t* lookup,
+                                        const int32_t* __restrict__ col, const double* __restrict__ weight,
+                                        int64_t v, int sum_mode, int32_t* __restrict__ alias,
+                                        double* __restrict__ probs, n2v_arc_t* __restrict__ arcs,
+                                        int32_t* __restrict__ scratch, unsigned long long* __restrict__ n_zero) {
+  const uint64_t base = vtx[v].base;
+  const uint32_t n = vtx[v].deg;
+  double* pr = probs + base;
+  n2v_arc_t* out = arcs + base;
+  // left-to-right fp64 sum of the raw weights, kept as float for the weighted return-edge fold
+  double wsum = 0.0;
+  for (uint32_t i = 0; i < n; ++i) {
+    const double w = weight[base + i];
+    pr[i] = w;
+    wsum = __dadd_rn(wsum, w);
+  }
+  vtx[v].wsum = static_cast<float>(wsum);
+  const bool ok = n2v::build_alias_one(pr, n, sum_mode, scratch + base,
+                                  [&](uint32_t i, int32_t a) { out[i].alias_idx = a; });
+  if (!ok) {
+    atomicAdd(n_zero, 1ull);
+    for (uint32_t i = 0; i < n; ++i) {
+      pr[i] = 0.0;
+      const int32_t x = col[base + i];
+      out[i] = n2v_arc_t{0xFFFFFFFFu, x, x, 0, lookup[x].base, lookup[x].deg, lookup[x].base, lookup[x].deg};
+      if (alias) alias[base + i] = 0;
+    }
+    return;
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    const int32_t a = out[i].alias_idx;
+    const double p = pr[i];
+    const int32_t self = col[base + i];
+    n2v_arc_t rec;
+    rec.thr = prob_to_thr(p);
+    rec.dst = self;
+    rec.alias_dst = (p >= 1.0) ? self : col[base + a];
+    rec.alias_idx = a;
+    // adjacency headers of both possible landing vertices (deg is final; base too: K0 ran before)
+    rec.dst_base = lookup[rec.dst].base;
+    rec.dst_deg = lookup[rec.dst].deg;
+    rec.adst_base = lookup[rec.alias_dst].base;
+    rec.adst_deg = lookup[rec.alias_dst].deg;
+    out[i] = rec;
+    if (alias) alias[base + i] = a;
+  }
+}
+
 __global__ void alias_build_kernel(n2v_vertex_t* __restrict__ vtx, const n2v_vertex_t* lookup,
                                    const int32_t* __restrict__ col,
                                    const double* __restrict__ weight, int64_t n_vertices, int sum_mode,
                                    int32_t* __restrict__ alias, double* __restrict__ probs,
                                    n2v_arc_t* __restrict__ arcs, int32_t* __restrict__ scratch,
                                    unsigned long long* __restrict__ n_zero, int32_t* __restrict__ hubs,
-                                   unsigned int* __restrict__ n_hubs) {
+                                   unsigned int* __restrict__ n_hubs, int32_t* __restrict__ giants,
+                                   unsigned int* __restrict__ n_giants) {
   for (int64_t v = blockIdx.x * int64_t(kBlock) + threadIdx.x; v < n_vertices;
        v += int64_t(gridDim.x) * kBlock) {
-    const uint64_t base = vtx[v].base;
     const uint32_t n = vtx[v].deg;
     if (n == 0) continue;
     if (n >= kHubMin && n <= kHubMax) {  // staged in shared memory by alias_hub_kernel
@@ -44,45 +93,45 @@ __global__ void alias_build_kernel(n2v_vertex_t* __restrict__ vtx, const n2v_ver
       hubs[slot] = static_cast<int32_t>(v);
       continue;
     }
-    double* pr = probs + base;
-    n2v_arc_t* out = arcs + base;
-    // left-to-right fp64 sum of the raw weights, kept as float for the weighted return-edge fold
-    double wsum = 0.0;
-    for (uint32_t i = 0; i < n; ++i) {
-      const double w = weight[base + i];
-      pr[i] = w;
-      wsum = __dadd_rn(wsum, w);
-    }
-    vtx[v].wsum = static_cast<float>(wsum);
-    const bool ok = n2v::build_alias_one(pr, n, sum_mode, scratch + base,
-                                    [&](uint32_t i, int32_t a) { out[i].alias_idx = a; });
-    if (!ok) {
-      atomicAdd(n_zero, 1ull);
-      for (uint32_t i = 0; i < n; ++i) {
-        pr[i] = 0.0;
-        const int32_t x = col[base + i];
-        out[i] = n2v_arc_t{0xFFFFFFFFu, x, x, 0, lookup[x].base, lookup[x].deg, lookup[x].base, lookup[x].deg};
-        if (alias) alias[base + i] = 0;
-      }
+    if (n > kHubMax) {                   // one CTA each in alias_giant_kernel
+      const unsigned int slot = atomicAdd(n_giants, 1u);
+      giants[slot] = static_cast<int32_t>(v);
       continue;
     }
-    for (uint32_t i = 0; i < n; ++i) {
-      const int32_t a = out[i].alias_idx;
-      const double p = pr[i];
-      const int32_t self = col[base + i];
-      n2v_arc_t rec;
-      rec.thr = prob_to_thr(p);
-      rec.dst = self;
-      rec.alias_dst = (p >= 1.0) ? self : col[base + a];
-      rec.alias_idx = a;
-      // adjacency headers of both possible landing vertices (deg is final; base too: K0 ran before)
-      rec.dst_base = lookup[rec.dst].base;
-      rec.dst_deg = lookup[rec.dst].deg;
-      rec.adst_base = lookup[rec.alias_dst].base;
-      rec.adst_deg = lookup[rec.alias_dst].deg;
-      out[i] = rec;
-      if (alias) alias[base + i] = a;
+    build_vertex_sequential(vtx, lookup, col, weight, v, sum_mode, alias, probs, arcs, scratch, n_zero);
+  }
+}
+
+// One CTA per vertex above the shared-memory limit (deg > kHubMax; the reference's default trim
+// cap is 100000, constants.py:6).  If every weight is exactly 1.0 the reference's construction is
+// trivial -- sum = n exactly, probs = 1.0, nothing on the underfull list, every alias stays 0 --
+// and the records are written in parallel.  Otherwise thread 0 runs the sequential construction.
+__global__ void __launch_bounds__(kHubBlock)
+alias_giant_kernel(n2v_vertex_t* __restrict__ vtx, const n2v_vertex_t* lookup, const int32_t* __restrict__ col,
+                   const double* __restrict__ weight, int sum_mode, int32_t* __restrict__ alias,
+                   double* __restrict__ probs, n2v_arc_t* __restrict__ arcs, int32_t* __restrict__ scratch,
+                   const int32_t* __restrict__ giants, const unsigned int* __restrict__ n_giants_ptr,
+                   unsigned long long* __restrict__ n_zero) {
+  const unsigned int n_giants = *n_giants_ptr;
+  for (unsigned int h = blockIdx.x; h < n_giants; h += gridDim.x) {
+    const int64_t v = giants[h];
+    const uint32_t base = vtx[v].base, n = vtx[v].deg;
+    int not_unit = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += kHubBlock) not_unit |= (weight[base + i] != 1.0) ? 1 : 0;
+    const bool unit = __syncthreads_or(not_unit) == 0;
+    if (unit) {
+      if (threadIdx.x == 0) vtx[v].wsum = static_cast<float>(static_cast<double>(n));
+      for (uint32_t i = threadIdx.x; i < n; i += kHubBlock) {
+        const int32_t self = col[base + i];
+        const uint32_t b = lookup[self].base, d = lookup[self].deg;
+        arcs[base + i] = n2v_arc_t{0xFFFFFFFFu, self, self, 0, b, d, b, d};
+        probs[base + i] = 1.0;
+        if (alias) alias[base + i] = 0;
+      }
+    } else if (threadIdx.x == 0) {
+      build_vertex_sequential(vtx, lookup, col, weight, v, sum_mode, alias, probs, arcs, scratch, n_zero);
     }
+    __syncthreads();
   }
 }
 
@@ -294,16 +343,25 @@ extern "C" int n2v_alias_build(n2v_vertex_t* vtx, const n2v_vertex_t* vtx_lookup
   N2V_CHECK_ARG(vtx && col && weight_sorted && probs && arcs && scratch, "n2v_alias_build: NULL buffer");
   // small device scratch: [0] zero-weight counter, [1] hub counter (as 2 x u32), then the hub list
   const int64_t max_hubs = n_arcs / kHubMin + 1;
+  const int64_t max_giants = n_arcs / (kHubMax + 1) + 1;
   unsigned long long* d_zero = nullptr;
-  N2V_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_zero), 16 + sizeof(int32_t) * max_hubs, stream));
+  N2V_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_zero), 16 + sizeof(int32_t) * (max_hubs + max_giants), stream));
   N2V_CUDA(cudaMemsetAsync(d_zero, 0, 16, stream));
   unsigned int* d_nhubs = reinterpret_cast<unsigned int*>(d_zero + 1);
+  unsigned int* d_ngiants = d_nhubs + 1;
   int32_t* d_hubs = reinterpret_cast<int32_t*>(d_zero + 2);
+  int32_t* d_giants = d_hubs + max_hubs;
   const n2v_vertex_t* lookup = vtx_lookup ? vtx_lookup : vtx;
   alias_build_kernel<<<grid_for(n_vertices), kBlock, 0, stream>>>(vtx, lookup, col, weight_sorted, n_vertices,
                                                                    sum_mode, alias, probs, arcs, scratch, d_zero,
-                                                                   d_hubs, d_nhubs);
+                                                                   d_hubs, d_nhubs, d_giants, d_ngiants);
   N2V_LAUNCH_OK();
+  if (n_arcs > kHubMax) {
+    const int64_t grid = max_giants < 4 * n2v::kSmCount ? max_giants : 4 * n2v::kSmCount;
+    alias_giant_kernel<<<static_cast<unsigned int>(grid), kHubBlock, 0, stream>>>(
+        vtx, lookup, col, weight_sorted, sum_mode, alias, probs, arcs, scratch, d_giants, d_ngiants, d_zero);
+    N2V_LAUNCH_OK();
+  }
   if (n_arcs >= kHubMin) {
     // the hub count stays on the device (no host round trip): one CTA per SM strides over the list and
     // exits at once when it is empty

@@ -33,7 +33,8 @@ __global__ void scatter_sorted(const uint64_t* __restrict__ keys, const uint32_t
                                const double* __restrict__ weight, int64_t n,
                                n2v_vertex_t* __restrict__ vtx, int32_t* __restrict__ col,
                                double* __restrict__ w_sorted, int64_t* __restrict__ perm,
-                               unsigned int* __restrict__ not_flags) {
+                               unsigned int* __restrict__ not_flags, const unsigned int* __restrict__ bad) {
+  if (*bad) return;   // pack_keys saw an id outside the graph: nothing below may index vtx[] with it
   unsigned int local = 0;
   for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) {
     const uint64_t k = keys[i];
@@ -56,7 +57,9 @@ __global__ void scatter_sorted(const uint64_t* __restrict__ keys, const uint32_t
 }
 
 // run ends -> vtx.deg (needs every base written: separate launch)
-__global__ void close_runs(const uint64_t* __restrict__ keys, int64_t n, n2v_vertex_t* __restrict__ vtx) {
+__global__ void close_runs(const uint64_t* __restrict__ keys, int64_t n, n2v_vertex_t* __restrict__ vtx,
+                           const unsigned int* __restrict__ bad) {
+  if (*bad) return;
   for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) {
     const uint32_t s = static_cast<uint32_t>(keys[i] >> 32);
     if (i + 1 == n || static_cast<uint32_t>(keys[i + 1] >> 32) != s)
@@ -67,7 +70,8 @@ __global__ void close_runs(const uint64_t* __restrict__ keys, int64_t n, n2v_ver
 // SYMMETRIC: every arc (a,b,w) has a mirror (b,a,w).  Only meaningful on SIMPLE graphs.
 __global__ void check_symmetric(const uint64_t* __restrict__ keys, const double* __restrict__ w_sorted,
                                 int64_t n, const n2v_vertex_t* __restrict__ vtx,
-                                unsigned int* __restrict__ not_flags) {
+                                unsigned int* __restrict__ not_flags, const unsigned int* __restrict__ bad_ids) {
+  if (*bad_ids) return;
   bool bad = false;
   for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) {
     const uint64_t k = keys[i];
@@ -157,12 +161,12 @@ extern "C" int n2v_csr_build(const int32_t* src, const int32_t* dst, const doubl
   N2V_CUDA(cub::DeviceRadixSort::SortPairs(base + L.cub, cub_bytes, dk, dv, n_arcs, 0, end_bit, stream));
 
   scatter_sorted<<<grid, kBlock, 0, stream>>>(dk.Current(), dv.Current(), weight, n_arcs, vtx, col,
-                                              weight_sorted, perm, dflags + 1);
+                                              weight_sorted, perm, dflags + 1, dflags);
   N2V_LAUNCH_OK();
-  close_runs<<<grid, kBlock, 0, stream>>>(dk.Current(), n_arcs, vtx);
+  close_runs<<<grid, kBlock, 0, stream>>>(dk.Current(), n_arcs, vtx, dflags);
   N2V_LAUNCH_OK();
   if (replicated) {
-    check_symmetric<<<grid, kBlock, 0, stream>>>(dk.Current(), weight_sorted, n_arcs, vtx, dflags + 1);
+    check_symmetric<<<grid, kBlock, 0, stream>>>(dk.Current(), weight_sorted, n_arcs, vtx, dflags + 1, dflags);
     N2V_LAUNCH_OK();
   }
 

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kBlock, 2) sgns_shared_kernel(const __grid_con
       bool keep = false;
       if (k < A.len) {
         tok = __ldg(A.walks + s * A.pitch + k);
-        if (tok >= 0) {
+        if (tok >= 0 && static_cast<uint32_t>(tok) < A.n_vertices) {   // ids beyond the table are out-of-vocabulary (gensim skips them)
           const uint32_t thr = __ldg(A.keep_thr + tok);
           if (thr == 0xFFFFFFFFu) keep = true;
           else if (thr != 0u) {

@@ -96,7 +96,7 @@ __device__ __noinline__ uint32_t exact_draw(const int32_t* __restrict__ vcol, co
   for (uint32_t i = 0; i < deg; ++i) {
     const int32_t x = vcol[i];
     const double a = (x == t) ? inv_p : (member_sorted(tcol, tdeg, x) ? 1.0 : inv_q);
-    total = __dadd_rn(total, __dmul_rn(vw[i], a));
+    total = __dadd_rn(total, __dmul_rn(vw ? vw[i] : 1.0, a));   // vw == NULL: unit-weight graph stored without weights
   }
   // 53-bit uniform in [0,1) from two 32-bit lanes
   const double u = __dmul_rn(__dadd_rn(__dmul_rn(static_cast<double>(r0 >> 5), 67108864.0),
@@ -108,7 +108,7 @@ __device__ __noinline__ uint32_t exact_draw(const int32_t* __restrict__ vcol, co
   for (uint32_t i = 0; i < deg; ++i) {
     const int32_t x = vcol[i];
     const double a = (x == t) ? inv_p : (member_sorted(tcol, tdeg, x) ? 1.0 : inv_q);
-    const double m = __dmul_rn(vw[i], a);
+    const double m = __dmul_rn(vw ? vw[i] : 1.0, a);
     run = __dadd_rn(run, m);
     if (m > 0.0) last = i;
     if (target < run) return i;
@@ -256,7 +256,7 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
       const uint4 r2 = n2v::philox4x32_10(A.key0, A.key1, wid_lo, wid_hi, static_cast<uint32_t>(pos), 0xFFFFFFFFu);
       const n2v_graph_part_t& PV = g.parts[MULTI ? part_v : 0];
       const n2v_graph_part_t& PT = g.parts[MULTI ? part_t : 0];
-      const uint32_t pick = exact_draw(PV.col + base_v, PV.weight + base_v, deg_v, t, PT.col + base_t, deg_t,
+      const uint32_t pick = exact_draw(PV.col + base_v, PV.weight ? PV.weight + base_v : nullptr, deg_v, t, PT.col + base_t, deg_t,
                                        A.inv_p, A.inv_q, r2.x, r2.y);
       x = PV.col[base_v + pick];
       arc_index = base_v + pick;

@@ -152,9 +152,14 @@ def trim_index(
             raise ValueError("tensor inputs must already be indexed (integer vertex ids): pass indexed=True")
         src, dst = df_graph[0], df_graph[1]
         w = df_graph[2] if len(df_graph) == 3 else None
+        # the reference's order: trim the arcs as listed (fugue.py:57-67), THEN expand to both
+        # directions (indexer.py:45-48) -- so a trimmed hub keeps its mirrored in-arcs and the
+        # graph stays symmetric.  (For frames the reference returns before the expansion when
+        # indexed=True, fugue.py:70-71; tensors are always indexed, so `directed` is honoured
+        # here -- INTEGRATION.md notes the difference.)
+        src, dst, w = trim_hotspots_device(src, dst, w, max_out_deg, random_seed)
         if directed is not True:
             src, dst, w = symmetrise_device(src, dst, w)
-        src, dst, w = trim_hotspots_device(src, dst, w, max_out_deg, random_seed)
         return ((src, dst) if w is None else (src, dst, w)), None
     cols = _columns(df_graph)
     if "src" not in cols or "dst" not in cols:
@@ -268,6 +273,9 @@ def random_walk(
     graph: Optional[DeviceGraph] = None,
     collect_stats: bool = False,
     out: Optional[torch.Tensor] = None,
+    process_group: Any = None,
+    n_vertices: Optional[int] = None,
+    assume_symmetric: bool = False,
 ) -> WalkFrame:
     """Second-order biased random walks; same contract as the reference (fugue.py:81-155).
 
@@ -282,7 +290,12 @@ def random_walk(
     Keyword-only extras: ``graph`` reuses a prebuilt DeviceGraph; ``collect_stats``; ``out`` is a
     pinned host int32 matrix ``[>= walkers, walk_length + 1]`` to receive the rows -- the walk then
     runs in chunks of start vertices whose device->host copies overlap the next chunk's kernel
-    (same rows as one launch), and ``WalkFrame.walks`` is a view of ``out``.
+    (same rows as one launch), and ``WalkFrame.walks`` is a view of ``out``.  ``process_group``
+    (torch.distributed, one process per GPU) selects the VERTEX-PARTITIONED graph: ``df_graph``
+    then holds only the arcs whose source lies in this rank's vertex range
+    ``[rank * ceil(n_vertices / G), ...)`` (global ids), every rank builds its part, peers read each
+    other's parts over NVLink, and the call returns this rank's rows (walks from its own start
+    vertices) -- the union over ranks is what one GPU holding the whole graph would return.
     """
     logging.info("random_walk(): start random walking ...")
     for param in NODE2VEC_PARAMS:
@@ -298,9 +311,17 @@ def random_walk(
     if num_walks < 1 or walk_length < 1:
         raise ValueError("num_walks and walk_length must be >= 1")
 
+    own_graph = None
     if graph is None:
         src, dst, weight = _graph_arrays(df_graph)
-        graph = DeviceGraph.from_arcs(src, dst, weight)
+        if process_group is not None:
+            from .graph import PartitionedGraph
+            if n_vertices is None:
+                raise ValueError("a vertex-partitioned walk needs n_vertices (the global vertex count)")
+            graph = own_graph = PartitionedGraph.from_local_arcs(src, dst, weight, int(n_vertices), group=process_group,
+                                                                 assume_symmetric=assume_symmetric)
+        else:
+            graph = DeviceGraph.from_arcs(src, dst, weight, n_vertices=n_vertices)
     start = graph.start_vertices()
     host = None
     if walk_seed is None:
@@ -308,5 +329,7 @@ def random_walk(
     else:
         walks, host, stats = _walk_from_seed_ids(graph, start, walk_seed, num_walks, walk_length, p, q, random_seed,
                                                  collect_stats, out)
+    if own_graph is not None:
+        own_graph.close()       # unmap the peers' parts, free the shareable buffers (collective)
     logging.info("random_walk(): random walking done ...")
     return WalkFrame(walks, walks_host=host, stats=stats)

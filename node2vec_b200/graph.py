@@ -25,6 +25,19 @@ def _as_device(x, device, np_dtype, torch_dtype) -> torch.Tensor:
 
 
 def _as_device_i32(x, device) -> torch.Tensor:
+    """Vertex ids as int32 on the device.  Wider integer inputs are range-checked first: a silent
+    wrap of an id >= 2^31 would alias a valid vertex (ids outside [0, V) are rejected by K0)."""
+    if isinstance(x, torch.Tensor):
+        if x.dtype in (torch.int64, torch.uint8, torch.int16) and x.numel():
+            lo, hi = int(x.min()), int(x.max())
+            if lo < -(1 << 31) or hi >= (1 << 31):
+                raise ValueError(f"vertex ids must fit int32, got range [{lo}, {hi}]")
+    else:
+        arr = np.asarray(x)
+        if arr.dtype.kind in "iu" and arr.dtype.itemsize > 4 and arr.size:
+            lo, hi = int(arr.min()), int(arr.max())
+            if lo < -(1 << 31) or hi >= (1 << 31):
+                raise ValueError(f"vertex ids must fit int32, got range [{lo}, {hi}]")
     return _as_device(x, device, np.int32, torch.int32)
 
 
@@ -338,8 +351,10 @@ class PartitionedGraph(DeviceGraph):
 
     @classmethod
     def from_local_arcs(cls, src, dst, weight, n_vertices: int, group=None, assume_symmetric: bool = False,
-                        sum_mode: str = "naive") -> "PartitionedGraph":
-        """src/dst/weight: the arcs whose src lies in this rank's range (global ids)."""
+                        sum_mode: str = "naive", keep_weight: bool = True) -> "PartitionedGraph":
+        """src/dst/weight: the arcs whose src lies in this rank's range (global ids).
+        ``keep_weight=False`` frees the fp64 weights (8 B/arc) after the build when every part is
+        unit-weight: the walk needs them only in its exact fallback, which then uses 1.0."""
         import torch.distributed as dist
         from . import dist as n2v_dist
         _lib.require_cuda()
@@ -362,7 +377,10 @@ class PartitionedGraph(DeviceGraph):
             g._ipc_ptrs = []
             vtx_local = torch.zeros((S, 4), dtype=torch.int32, device=device)
             g.col, p = _ipc_tensor(lib, (A,), torch.int32, device); g._ipc_ptrs.append(p)
-            g.weight, p = _ipc_tensor(lib, (A,), torch.float64, device); g._ipc_ptrs.append(p)
+            if keep_weight:
+                g.weight, p = _ipc_tensor(lib, (A,), torch.float64, device); g._ipc_ptrs.append(p)
+            else:
+                g.weight = torch.empty(A, dtype=torch.float64, device=device); g._ipc_ptrs.append(0)
             nbytes = int(lib.n2v_csr_scratch_bytes(A, S))
             scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
             flags = C.c_uint32(0)
@@ -401,11 +419,20 @@ class PartitionedGraph(DeviceGraph):
             if assume_symmetric and (g.flags & _lib.GRAPH_SIMPLE):
                 g.flags |= _lib.GRAPH_SYMMETRIC
             g.n_vertices, g.n_arcs, g.n_local_arcs = int(n_vertices), int(totals.item()), A
+            if not keep_weight:
+                if g.flags & _lib.GRAPH_UNIT_WEIGHT:
+                    g.weight = None                      # every part is unit-weight: nobody reads them
+                else:                                    # weights matter after all: move them to a shareable buffer
+                    shared_w, p = _ipc_tensor(lib, (A,), torch.float64, device)
+                    shared_w.copy_(g.weight)
+                    g.weight, g._ipc_ptrs[1] = shared_w, p
+                    torch.cuda.synchronize()
             # export shareable handles, hand the peers their own copies of the fds, map their parts
             import struct
             handles, my_fds = [], []
             own = {"arcs": g._ipc_ptrs[3], "col": g._ipc_ptrs[0], "weight": g._ipc_ptrs[1], "hash": g._ipc_ptrs[2]}
-            for name in ("arcs", "col", "weight", "hash"):
+            shared = ("arcs", "col", "hash") if g.weight is None else ("arcs", "col", "weight", "hash")
+            for name in shared:
                 buf = C.create_string_buffer(64)
                 _lib.check(lib.n2v_ipc_export(C.c_void_p(own[name]), buf), "n2v_ipc_export")
                 handles.append(bytes(buf.raw))
@@ -424,18 +451,19 @@ class PartitionedGraph(DeviceGraph):
             for p_idx in range(G):
                 st.parts[p_idx].vtx = g.vtx.data_ptr() + p_idx * S * 16
                 if p_idx == rank:
-                    ptrs = [g.arcs.data_ptr(), g.col.data_ptr(), g.weight.data_ptr(), g.hash.data_ptr()]
+                    ptrs = {"arcs": g.arcs.data_ptr(), "col": g.col.data_ptr(), "hash": g.hash.data_ptr(),
+                            "weight": None if g.weight is None else g.weight.data_ptr()}
                 else:
-                    ptrs = []
-                    for h, fd in zip(all_handles[p_idx], peer_fds[p_idx]):
+                    ptrs = {"weight": None}
+                    for name, h, fd in zip(shared, all_handles[p_idx], peer_fds[p_idx]):
                         local_h = struct.pack("<i", fd) + h[4:]          # the fd as it is known in THIS process
                         out = C.c_void_p()
                         _lib.check(lib.n2v_ipc_open(local_h, C.byref(out)), "n2v_ipc_open")
                         os.close(fd)
-                        ptrs.append(int(out.value))
+                        ptrs[name] = int(out.value)
                         g._peer_ptrs.append(int(out.value))
-                st.parts[p_idx].arcs, st.parts[p_idx].col = ptrs[0], ptrs[1]
-                st.parts[p_idx].weight, st.parts[p_idx].hash = ptrs[2], ptrs[3]
+                st.parts[p_idx].arcs, st.parts[p_idx].col = ptrs["arcs"], ptrs["col"]
+                st.parts[p_idx].weight, st.parts[p_idx].hash = ptrs["weight"], ptrs["hash"]
             g._struct = st
             for fd in my_fds:
                 os.close(fd)
@@ -449,7 +477,8 @@ class PartitionedGraph(DeviceGraph):
         return (torch.nonzero(own != 0).view(-1) + self.v_lo).to(torch.int32)
 
     def nbytes(self) -> int:
-        return sum(int(t.numel()) * t.element_size() for t in (self.vtx, self.arcs, self.col, self.weight, self.hash))
+        return sum(int(t.numel()) * t.element_size() for t in (self.vtx, self.arcs, self.col, self.weight, self.hash)
+                   if t is not None)
 
     def close(self) -> None:
         """Unmap peers' parts and free this rank's shareable buffers (after a barrier)."""
@@ -463,5 +492,6 @@ class PartitionedGraph(DeviceGraph):
             dist.barrier(group=self.group)
         self.arcs = self.col = self.weight = self.hash = None
         for p in getattr(self, "_ipc_ptrs", []):
-            lib.n2v_ipc_free(C.c_void_p(p))
+            if p:
+                lib.n2v_ipc_free(C.c_void_p(p))
         self._ipc_ptrs = []

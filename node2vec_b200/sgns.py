@@ -173,6 +173,8 @@ class Word2Vec(object):
         self.syn0 = self.syn1neg = None      # device tables [n_rows, size]
         self._ids = None                     # row -> vertex id when the id space was densified
         if sentences is not None:
+            # one host->device copy of the corpus serves both passes
+            sentences = _walk_matrix(sentences, torch.device("cuda", torch.cuda.current_device()))
             self.build_vocab(sentences)
             self.train(sentences)
 
@@ -235,11 +237,16 @@ class Word2Vec(object):
 
     # ------------------------------------------------------------------ training (K3)
     def train(self, sentences, epochs: Optional[int] = None, trace_cap: int = 0,
-              epoch_range: Optional[Tuple[int, int]] = None, **ignored):
+              epoch_range: Optional[Tuple[int, int]] = None, walk_range: Optional[Tuple[int, int]] = None,
+              sync: Optional[bool] = None, **ignored):
         """Run ``epochs`` (default ``iter``) epochs.  Returns (pairs trained, tokens kept).
         ``epoch_range=(a, b)`` runs only epochs a..b-1 of that ``epochs``-long schedule (learning-rate
         decay and random streams are functions of the epoch index), so training can be checkpointed
-        with ``save`` between epochs and resumed after ``load`` with the remaining range."""
+        with ``save`` between epochs and resumed after ``load`` with the remaining range.
+        ``walk_range=(lo, hi)`` trains on rows lo..hi-1 only (a slice of the epoch: learning rate and
+        random streams are functions of the row's global index, so slices compose to the epoch).
+        ``sync`` overrides the data-parallel averaging decision for this call (None = every
+        ``sync_every`` epochs and after the last one)."""
         lib = _lib.load()
         if self.syn0 is None:
             raise RuntimeError("you must first build vocabulary before training the model")
@@ -259,15 +266,23 @@ class Word2Vec(object):
             first, last = (0, epochs) if epoch_range is None else (int(epoch_range[0]), int(epoch_range[1]))
             if not 0 <= first <= last <= epochs:
                 raise ValueError(f"epoch_range {epoch_range} must lie inside [0, {epochs}]")
+            rows = walks
+            if walk_range is not None:
+                lo, hi = int(walk_range[0]), int(walk_range[1])
+                if not 0 <= lo <= hi <= walks.shape[0]:
+                    raise ValueError(f"walk_range {walk_range} must lie inside [0, {walks.shape[0]}]")
+                rows = walks[lo:hi]
+                P.walk_offset = self._walk_offset + lo
             for ep in range(first, last):
                 P.epoch = ep
                 entry = lib.n2v_sgns_train_shared if getattr(self, "share_negatives", False) else lib.n2v_sgns_train
-                _lib.check(entry(_lib.ptr(walks), walks.shape[0], walks.shape[1], walks.stride(0),
+                _lib.check(entry(_lib.ptr(rows), rows.shape[0], walks.shape[1], walks.stride(0),
                                  _lib.ptr(self._keep), _lib.ptr(self._neg), self._n_rows,
                                  _lib.ptr(self.syn0), _lib.ptr(self.syn1neg), _lib.ptr(self._exp),
                                  C.byref(P), _lib.ptr(stats), _lib.ptr(trace), _lib.ptr(trace_alpha),
                                  trace_cap, _lib.current_stream_ptr()), "n2v_sgns_train")
-                if self.process_group is not None and ((ep + 1) % self.sync_every == 0 or ep + 1 == epochs):
+                due = ((ep + 1) % self.sync_every == 0 or ep + 1 == epochs) if sync is None else bool(sync)
+                if self.process_group is not None and due:
                     self.average_tables()
         st = dict(zip(_lib.SGNS_STAT_NAMES, stats.cpu().tolist()))
         self.train_stats = st

@@ -103,6 +103,87 @@ def rmat_device(scale: int, edge_factor: int = 16, seed: int = 42, device=None,
     return torch.cat([lo, hi]).to(torch.int32), torch.cat([hi, lo]).to(torch.int32)
 
 
+def rmat_hotspot_edges_device(scale: int = 20, edge_factor: int = 16, seed: int = 42, device=None,
+                              hotspots: int = 16, hotspot_degree: int = 1 << 18):
+    """BASELINE configs[2] input: the UNDIRECTED edge list (every edge once, src < dst, unique,
+    loop-free) of an R-MAT graph with injected hotspot vertices -- the shape a reference user
+    hands to ``trim_index(..., directed=False, max_out_deg=...)``, which trims the listed
+    direction first and symmetrises afterwards (fugue.py:57-77, indexer.py:45-48)."""
+    import torch
+    src, dst = rmat_device(scale, edge_factor, seed, device, hotspots=hotspots, hotspot_degree=hotspot_degree)
+    half = src.numel() // 2          # rmat_device returns [lo..., hi...] / [hi..., lo...]
+    return src[:half].contiguous(), dst[:half].contiguous()
+
+
+RMAT_BLOCKS = 64
+
+
+def _rmat_keys(scale, n_edges, seed, device, abcd=(0.57, 0.19, 0.19, 0.05), chunk=1 << 26):
+    """n_edges R-MAT edges as int64 keys (src << 32 | dst), ids scrambled by an affine bijection."""
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    a, b, c, _ = abcd
+    n = 1 << scale
+    mult = 0x9E3779B1 | 1                               # odd => bijection mod 2^scale
+    out = torch.empty(n_edges, dtype=torch.int64, device=device)
+    for lo in range(0, n_edges, chunk):
+        m = min(chunk, n_edges - lo)
+        src = torch.zeros(m, dtype=torch.int64, device=device)
+        dst = torch.zeros(m, dtype=torch.int64, device=device)
+        for _ in range(scale):
+            r = torch.rand(m, device=device, generator=gen)
+            src = (src << 1) | (r >= a + b).long()
+            dst = (dst << 1) | (((r >= a) & (r < a + b)) | (r >= a + b + c)).long()
+        src = (src * mult + 12345) & (n - 1)
+        dst = (dst * mult + 12345) & (n - 1)
+        out[lo:lo + m] = (src << 32) | dst
+        del src, dst, r
+    return out
+
+
+def rmat_partition_device(scale: int, edge_factor: int, rank: int, world: int, device, seed: int = 1000,
+                          group=None):
+    """BASELINE configs[4] input, generated where it will live: every rank draws 1/world of the
+    R-MAT edges, both directions are routed to the owner of their source vertex (vertex ranges of
+    ceil(V / world)) with one all-to-all, duplicates and self loops are dropped locally.
+    Returns this rank's arcs (src, dst) as int32 CUDA tensors sorted by (src, dst)."""
+    import torch
+    import torch.distributed as dist
+    V = 1 << scale
+    S = (V + world - 1) // world
+    n_edges = edge_factor << scale
+    # the edge multiset is drawn in RMAT_BLOCKS fixed blocks (block b under seed + b), dealt round-robin
+    # to the ranks: the GRAPH is the same for every world size (strong scaling on one fixed graph)
+    blocks = [b for b in range(RMAT_BLOCKS) if b % world == rank]
+    sizes = [n_edges * (b + 1) // RMAT_BLOCKS - n_edges * b // RMAT_BLOCKS for b in blocks]
+    keys = torch.empty(sum(sizes), dtype=torch.int64, device=device)
+    at = 0
+    for b, m in zip(blocks, sizes):
+        keys[at:at + m] = _rmat_keys(scale, m, seed + b, device)
+        at += m
+    keys = keys[(keys >> 32) != (keys & 0xFFFFFFFF)]                        # no self loops
+    keys = torch.cat([keys, ((keys & 0xFFFFFFFF) << 32) | (keys >> 32)])    # both directions
+    if world > 1:
+        owner = torch.div(keys >> 32, S, rounding_mode="floor")
+        send_counts = torch.bincount(owner, minlength=world)
+        order = torch.argsort(owner)
+        del owner
+        keys = keys[order]
+        del order
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+        recv = torch.empty(int(recv_counts.sum()), dtype=torch.int64, device=device)
+        dist.all_to_all_single(recv, keys, output_split_sizes=recv_counts.tolist(),
+                               input_split_sizes=send_counts.tolist(), group=group)
+        keys = recv
+        del recv
+    keys = torch.unique(keys)                                               # simple graph; sorted by (src, dst)
+    src = (keys >> 32).to(torch.int32)
+    dst = (keys & 0xFFFFFFFF).to(torch.int32)
+    return src, dst
+
+
 def products_like_device(n: int = 2449029, n_edges: int = 61859140, seed: int = 42, device=None):
     """BASELINE configs[3]: an ogbn-products-shaped graph (2.4 M vertices, ~62 M undirected edges):
     R-MAT scale 22 folded onto n vertices.  Returns symmetrised int32 CUDA tensors."""

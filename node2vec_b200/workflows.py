@@ -167,8 +167,18 @@ def rewalk(prev: WalkFrame, graph: DeviceGraph, changed_ids: Sequence[int], n2v_
     if old.numel() and old.shape[1] != int(prm["walk_length"]) + 1:
         raise ValueError("prev was walked with another walk_length")
     changed = torch.as_tensor(np.unique(np.asarray(list(changed_ids), dtype=np.int64)), device=dev)
-    stale = torch.unique(torch.cat([stale_start_vertices(old, changed), changed]))
     start = graph.start_vertices()
+    # walkers the OLD run dropped at a sink (fugue.py:147) left no row in `prev`: a sink that gained
+    # out-arcs would let them live now, so every start vertex holding fewer than num_walks rows --
+    # or none at all -- is re-walked as well
+    num_walks = int(prm["num_walks"])
+    if old.numel():
+        owners, rows = torch.unique(old[:, 0].to(torch.int64), return_counts=True)
+        short = owners[rows < num_walks]
+        absent = start.to(torch.int64)[~torch.isin(start.to(torch.int64), owners)]
+    else:
+        short, absent = torch.zeros(0, dtype=torch.int64, device=dev), start.to(torch.int64)
+    stale = torch.unique(torch.cat([stale_start_vertices(old, changed), changed, short, absent]))
     redo = start[torch.isin(start.to(torch.int64), stale)]
     fresh = _walk_alive(graph, redo, prm, random_seed)
     keep = old[~torch.isin(old[:, 0].to(torch.int64), stale)] if old.numel() else old.reshape(0, fresh.shape[1])

@@ -11,7 +11,7 @@ from node2vec_b200.graph import DeviceGraph, walk_to_host
 
 name = sys.argv[1] if len(sys.argv) > 1 else "blogcatalog_like"
 w = bench.WORKLOADS[name]
-src, dst = bench.make_graph(name)
+src, dst = bench.make_graph_host(name)
 src_pin, dst_pin = torch.as_tensor(src).pin_memory(), torch.as_tensor(dst).pin_memory()
 
 

@@ -9,7 +9,7 @@ from node2vec_b200.sgns import Word2Vec
 
 name = sys.argv[1] if len(sys.argv) > 1 else "blogcatalog_like"
 w = bench.WORKLOADS[name]
-src, dst = bench.make_graph(name)
+src, dst = bench.make_graph_host(name)
 torch.cuda.synchronize()
 
 

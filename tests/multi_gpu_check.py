@@ -37,7 +37,8 @@ def main():
         S = (V + world - 1) // world
         mine = (s >= rank * S) & (s < (rank + 1) * S)
         part = PartitionedGraph.from_local_arcs(s[mine], d[mine], None if w is None else w[mine], V,
-                                                assume_symmetric=sym)
+                                                assume_symmetric=sym, keep_weight=False)
+        assert (part.weight is None) == (w is None)          # unit-weight parts drop their fp64 weights
         assert part.flags == full.flags, (name, part.flags, full.flags)
         start = part.start_vertices()
         want_start = full.start_vertices()

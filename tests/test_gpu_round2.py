@@ -1,0 +1,256 @@
+"""Round-2 GPU parity gates (all through the C ABI):
+
+* chi-square of device transition frequencies against the reference's law
+  (randomwalk.py:219-231) on BASELINE-sized graphs -- ER-10k and the BlogCatalog-shaped graph at
+  (p, q) in {(1,1), (1,.5), (.25,4), (4,.25)} -- conditioned on the highest-traffic (t, v) pairs AND
+  on hub v with degree > 1000 (the fp32 fold threshold and the two-threshold skip at large degree);
+* giant (> 12288 arcs) unit-weight vertices through the parallel alias path, bit-exact;
+* vertex ids outside the graph raise instead of faulting; out-of-vocabulary tokens are skipped;
+* the reference's trim -> symmetrise order on arc tensors; rewalk after a sink gains out-arcs.
+"""
+import numpy as np
+import pytest
+
+from oracle import clib, ref_walk
+from tests.helpers import chi_square_ok, pack_arcs
+
+pytestmark = pytest.mark.gpu
+
+ALPHA = 1e-4          # per-test significance of the chi-square gates (the stated tolerance)
+
+
+@pytest.fixture(scope="module")
+def n2v():
+    import torch
+    assert torch.cuda.is_available()
+    from node2vec_b200 import _lib, fugue, graph, synth, workflows
+    _lib.load()
+
+    class NS:
+        pass
+    ns = NS()
+    ns.torch, ns.lib, ns.graph, ns.fugue, ns.synth, ns.workflows = torch, _lib, graph, fugue, synth, workflows
+    return ns
+
+
+_GRAPHS = {}
+
+
+def _bench_graph(n2v, name):
+    """(DeviceGraph, row_ptr, col) of a BASELINE graph, cached per module."""
+    if name not in _GRAPHS:
+        if name == "er_10k":
+            src, dst = n2v.synth.erdos_renyi(10000, 100000, seed=42)
+        else:
+            src, dst = n2v.synth.blogcatalog_like(10000, 334000, seed=42)
+        g = n2v.graph.DeviceGraph.from_arcs(src, dst, None, n_vertices=10000)
+        row_ptr, col, _, _ = clib.csr_from_arcs(src, dst, None, 10000)
+        _GRAPHS[name] = (g, row_ptr, col)
+    return _GRAPHS[name]
+
+
+def _law(row_ptr, col, t, v, p, q):
+    """The reference's next-vertex law at (t, v) on a unit-weight graph (randomwalk.py:219-231):
+    weight / p back to t, weight into N_out(t), weight / q elsewhere, normalised."""
+    nb = col[row_ptr[v]:row_ptr[v + 1]]
+    nt = col[row_ptr[t]:row_ptr[t + 1]]
+    wts = np.where(nb == t, 1.0 / p, np.where(np.isin(nb, nt), 1.0, 1.0 / q))
+    return nb, wts / wts.sum()
+
+
+@pytest.mark.parametrize("name", ["er_10k", "blogcatalog_like"])
+@pytest.mark.parametrize("p,q", [(1.0, 1.0), (1.0, 0.5), (0.25, 4.0), (4.0, 0.25)])
+def test_transition_frequencies_at_baseline_size(n2v, name, p, q):
+    torch = n2v.torch
+    g, row_ptr, col = _bench_graph(n2v, name)
+    deg = np.diff(row_ptr)
+    # cross-check the vectorised law against the oracle's restatement on one pair
+    t0 = int(np.argmax(deg)); v0 = int(col[row_ptr[t0]])
+    adj = {u: (col[row_ptr[u]:row_ptr[u + 1]].tolist(), [1.0] * int(deg[u])) for u in (t0, v0)}
+    nb, pr = _law(row_ptr, col, t0, v0, p, q)
+    want = ref_walk.transition_law(adj, t0, v0, p, q)
+    assert np.allclose(pr, [want[int(x)] for x in nb], rtol=1e-12)
+
+    # (a) the highest-traffic (t, v) pairs of a BASELINE-shaped run
+    start = g.start_vertices()
+    walks, alive, _ = g.walk(start, 40, 12, p, q, seed=1234)
+    assert bool(alive.all())
+    w = walks.long()
+    trip = torch.stack([w[:, :-2].reshape(-1), w[:, 1:-1].reshape(-1), w[:, 2:].reshape(-1)], 1)
+    key = trip[:, 0] * 10000 + trip[:, 1]
+    uniq, cnt = torch.unique(key, return_counts=True)
+    top = uniq[torch.argsort(cnt, descending=True)[:6]].cpu().tolist()
+    pairs = [(k // 10000, k % 10000) for k in top]
+    # (b) hubs: the largest-degree v, entered from its lowest-degree neighbour t (so a walker started at t
+    # lands on v with probability 1 / deg(t)); includes deg(v) > 1000 on the BlogCatalog-shaped graph
+    hubs = np.argsort(-deg)[:3]
+    for v in hubs:
+        nbv = col[row_ptr[v]:row_ptr[v + 1]]
+        t = int(nbv[np.argmin(deg[nbv])])
+        pairs.append((t, int(v)))
+    if name == "blogcatalog_like":
+        assert deg[hubs[0]] > 1000
+    for t, v in pairs:
+        n_walkers = int(min(3_000_000, max(200_000, 300 * deg[v] * deg[t])))
+        ws, al, _ = g.walk(torch.tensor([t], dtype=torch.int32, device="cuda"), n_walkers, 2, p, q, seed=99 + t)
+        ws = ws[al]
+        x = ws[ws[:, 1] == v][:, 2].cpu().numpy()
+        nb, pr = _law(row_ptr, col, t, v, p, q)
+        assert np.isin(x, nb).all()
+        counts = np.bincount(np.searchsorted(nb, x), minlength=len(nb))
+        ok, pval = chi_square_ok(counts, pr, ALPHA)
+        assert ok, (name, p, q, t, v, int(deg[v]), len(x), pval)
+        # the return arc on its own (fold component): binomial z-score
+        k = int(counts[np.searchsorted(nb, t)]); n = len(x); pt = float(pr[np.searchsorted(nb, t)])
+        z = (k - n * pt) / max(np.sqrt(n * pt * (1 - pt)), 1e-9)
+        assert abs(z) < 4.5, (name, p, q, t, v, k, n * pt, z)
+
+
+def test_alias_giant_unit_and_weighted_hubs_bit_exact(n2v):
+    """Vertices beyond the shared-memory path (deg > 12288): all-1.0 weights take the parallel
+    trivial construction, anything else the sequential one -- both bit-exact vs the oracle."""
+    rng = np.random.default_rng(3)
+    n = 70000
+    src = [rng.integers(0, n, 40000)]; dst = [rng.integers(0, n, 40000)]; w = [rng.uniform(0.5, 2.0, 40000)]
+    for v, d, unit in ((5, 20000, True), (6, 65537, True), (7, 13000, False), (8, 12289, True)):
+        src.append(np.full(d, v)); dst.append(rng.permutation(n)[:d]); w.append(np.ones(d) if unit else rng.uniform(0.5, 2, d))
+    src, dst, w = np.concatenate(src), np.concatenate(dst), np.concatenate(w)
+    w[-3] = 1.0000000000000002                      # vertex 8: one weight an ulp off 1.0 -> sequential path
+    for mode in ("naive", "neumaier"):
+        g = n2v.graph.DeviceGraph.from_arcs(src, dst, w, n_vertices=n, sum_mode=mode, keep_tables=True)
+        row_ptr, col, ws, _ = clib.csr_from_arcs(src, dst, w, n)
+        alias, probs, bad = clib.alias_tables_csr(row_ptr, ws, mode, threads=4)
+        h = g.to_host()
+        assert bad == 0 and np.array_equal(h["alias"], alias)
+        assert np.array_equal(h["probs"].view(np.uint64), probs.view(np.uint64))
+        thr, adst, aalias = pack_arcs(row_ptr, col, alias, probs)
+        assert np.array_equal(h["thr"], thr) and np.array_equal(h["dst"], adst) and np.array_equal(h["alias_dst"], aalias)
+        assert np.array_equal(h["dst_deg"], h["deg"][adst]) and np.array_equal(h["adst_deg"], h["deg"][aalias])
+        assert h["wsum"][5] == np.float32(20000.0) and h["wsum"][6] == np.float32(65537.0)
+
+
+def test_bad_vertex_ids_raise_and_do_not_poison_the_context(n2v):
+    torch = n2v.torch
+    src = np.array([0, 1, 2, -1, 3], dtype=np.int64); dst = np.array([1, 2, 3, 0, 0], dtype=np.int64)
+    with pytest.raises(ValueError):
+        n2v.graph.DeviceGraph.from_arcs(src, dst, None, n_vertices=4)
+    with pytest.raises(ValueError):
+        n2v.graph.DeviceGraph.from_arcs(np.array([0, 7]), np.array([1, 0]), None, n_vertices=4)
+    with pytest.raises(ValueError):                      # would wrap to a valid int32 id
+        n2v.graph.DeviceGraph.from_arcs(np.array([0, (1 << 32) + 1]), np.array([1, 0]), None, n_vertices=4)
+    with pytest.raises(ValueError):
+        n2v.graph.DeviceGraph.from_arcs(torch.tensor([0, 1 << 33], device="cuda"), torch.tensor([1, 0], device="cuda"),
+                                        None, n_vertices=4)
+    torch.cuda.synchronize()                             # no sticky fault: the context still works
+    g = n2v.graph.DeviceGraph.from_arcs(np.array([0, 1]), np.array([1, 0]), None, n_vertices=2)
+    walks, alive, _ = g.walk(g.start_vertices(), 2, 3, seed=1)
+    assert walks.cpu().numpy().tolist() == [[0, 1, 0, 1], [0, 1, 0, 1], [1, 0, 1, 0], [1, 0, 1, 0]]
+
+
+def test_sgns_tokens_beyond_the_table_are_out_of_vocabulary(n2v):
+    """gensim skips tokens it has no vocabulary entry for; ids >= the table size fixed by
+    build_vocab must be skipped too, never dereferenced."""
+    torch = n2v.torch
+    from node2vec_b200.sgns import Word2Vec
+    gen = torch.Generator(device="cuda"); gen.manual_seed(0)
+    walks = torch.randint(0, 100, (512, 21), device="cuda", dtype=torch.int32, generator=gen)
+    m = Word2Vec(size=32, sg=1, negative=5, min_count=1, iter=1, seed=3, sample=0.0)
+    m.build_vocab(walks)
+    dirty = walks.clone()
+    dirty[::3, 5] = 1_000_000
+    dirty[1::7, 0] = 2_000_000_000
+    clean = dirty.clone()
+    clean[dirty >= 100] = -1
+    before = m.syn0.clone()
+    pairs_dirty, kept_dirty = m.train(dirty, epochs=1)
+    after_dirty = m.syn0.clone()
+    m2 = Word2Vec(size=32, sg=1, negative=5, min_count=1, iter=1, seed=3, sample=0.0)
+    m2.build_vocab(walks)
+    assert torch.equal(m2.syn0, before)
+    pairs_clean, kept_clean = m2.train(clean, epochs=1)
+    assert (pairs_dirty, kept_dirty) == (pairs_clean, kept_clean) and kept_dirty < dirty.numel()
+    assert bool(torch.isfinite(after_dirty).all())
+
+
+def test_trim_index_on_tensors_follows_the_reference_order(n2v):
+    """trim the arcs as listed, THEN expand to both directions (fugue.py:57-77 + indexer.py:45-48):
+    the arc set equals the pandas path's (mapped back through its name table), and the graph is
+    symmetric although a hub was trimmed."""
+    import pandas as pd
+    torch = n2v.torch
+    rng = np.random.default_rng(4)
+    a = rng.integers(0, 300, 4000); b = rng.integers(0, 300, 4000)
+    hub = np.full(900, 7); other = rng.permutation(np.arange(300, 1300))[:900]
+    lo = np.concatenate([np.minimum(a, b), hub]); hi = np.concatenate([np.maximum(a, b), other])
+    key = np.unique((lo.astype(np.int64) << 32 | hi)[lo != hi])
+    lo, hi = (key >> 32), (key & 0xFFFFFFFF)
+    perm = rng.permutation(len(lo)); lo, hi = lo[perm], hi[perm]
+    ts, td = torch.as_tensor(lo, device="cuda").int(), torch.as_tensor(hi, device="cuda").int()
+    (s, d), none = n2v.fugue.trim_index(None, (ts, td), indexed=True, directed=False, max_out_deg=100, random_seed=3)
+    assert none is None
+    got = set(zip(s.cpu().tolist(), d.cpu().tolist()))
+    frame, names = n2v.fugue.trim_index(None, pd.DataFrame({"src": lo, "dst": hi}), indexed=False, directed=False,
+                                        max_out_deg=100, random_seed=3)
+    nm = dict(zip(names.as_pandas()["vertex_id"].tolist(), names.as_pandas()["vertex_name"].tolist()))
+    f = frame.as_pandas()
+    want = set(zip((nm[i] for i in f["src"].tolist()), (nm[i] for i in f["dst"].tolist())))
+    assert got == want and len(got) == len(s)
+    g = n2v.graph.DeviceGraph.from_arcs(s, d, None, n_vertices=1300)
+    assert g.flags & 7 == 7                                         # unit, SYMMETRIC, simple
+    deg = g.degrees().cpu().numpy()
+    assert deg[7] >= 100                                            # 100 kept out-arcs + mirrored in-arcs
+
+
+def test_rewalk_revives_walkers_that_died_at_a_former_sink(n2v):
+    """a -> z with z a sink drops the walkers started at a (fugue.py:147); once z gains z -> b a full
+    walk of the new graph has those rows, so the incremental re-walk must produce them too."""
+    torch = n2v.torch
+    src = np.array([0, 1, 1, 2, 3], dtype=np.int64); dst = np.array([4, 2, 3, 1, 1], dtype=np.int64)   # 4 = sink
+    prm = {"num_walks": 3, "walk_length": 4, "return_param": 1.0, "inout_param": 1.0}
+    old = n2v.fugue.random_walk(None, (src, dst), dict(prm), None, random_seed=5)
+    assert 0 not in old.walks[:, 0]                                 # every walker from 0 died at vertex 4
+    src2, dst2 = np.append(src, 4), np.append(dst, 1)
+    g2 = n2v.graph.DeviceGraph.from_arcs(src2, dst2, None, n_vertices=5)
+    full = n2v.fugue.random_walk(None, None, dict(prm), None, random_seed=5, graph=g2)
+    inc, info = n2v.workflows.rewalk(old, g2, [4], dict(prm), 5)
+    assert np.array_equal(inc.walks, full.walks) and (full.walks[:, 0] == 0).sum() == 3
+
+
+@pytest.mark.parametrize("name", ["er_10k", "blogcatalog_like"])
+def test_auc_gate_on_baseline_configs(n2v, name):
+    """north_star gate at BASELINE sizes, through the reference-shaped API: embeddings from
+    ``Node2VecGensim(...).fit()`` (D = 128, window 5, 5 negatives) reach the link-prediction AUC of the
+    gensim-3.8 restatement trained on the SAME walk matrix within +-0.01 (mean of 3 seeds).
+    configs[0]: ER 10k/100k, p=1 q=.5, 10 x 20.  configs[1] shape: BlogCatalog-like 10k/334k,
+    p=.25 q=4, 10 walks x 40 (the bench uses 80 walks; 10 keep the CPU side of the gate short)."""
+    import os
+    from node2vec_b200.embedding import Node2VecGensim
+    from oracle import linkpred
+    if name == "er_10k":
+        src, dst = n2v.synth.erdos_renyi(10000, 100000, seed=42)
+        prm = {"num_walks": 10, "walk_length": 20, "return_param": 1.0, "inout_param": 0.5}
+    else:
+        src, dst = n2v.synth.blogcatalog_like(10000, 334000, seed=42)
+        prm = {"num_walks": 10, "walk_length": 40, "return_param": 0.25, "inout_param": 4.0}
+    n, half = 10000, len(src) // 2
+    edges = np.stack([src[:half], dst[:half]], axis=1).astype(np.int64)
+    train, pos, neg = linkpred.split_edges(edges, n, 0.1, 0)
+    s = np.concatenate([train[:, 0], train[:, 1]]); d = np.concatenate([train[:, 1], train[:, 0]])
+    res = n2v.fugue.random_walk(None, (s, d), dict(prm), random_seed=5)
+    walks = res.walks
+    counts = np.bincount(walks.reshape(-1), minlength=n)
+    hp = dict(window=5, negative=5, alpha=0.025, min_alpha=1e-4, min_count=1, sample=1e-3)
+    epochs = 3
+    threads = max(1, min(32, os.cpu_count() or 1))
+    auc_ref, auc_gpu = [], []
+    for seed in (1, 2, 3):
+        syn0, syn1 = clib.sgns_init(n, 128, seed)
+        clib.sgns_train(walks, counts, syn0, syn1, epochs=epochs, seed=seed, batch_words=1000, threads=threads, **hp)
+        auc_ref.append(linkpred.auc_dot(syn0, pos, neg))
+        model = Node2VecGensim(res, {"sg": 1, "negative": 5, "iter": epochs, "min_count": 1}, window_size=5,
+                               vector_size=128, random_seed=seed).fit()
+        emb = np.zeros((n, 128), dtype=np.float32)
+        emb[[int(t) for t in model.wv.index2word]] = model.wv.vectors
+        auc_gpu.append(linkpred.auc_dot(emb, pos, neg))
+    print(f"[{name}] AUC restatement {auc_ref} device {auc_gpu}")
+    assert abs(np.mean(auc_gpu) - np.mean(auc_ref)) <= 0.01, (name, auc_gpu, auc_ref)
