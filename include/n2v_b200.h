@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define N2V_ABI_VERSION 6
+#define N2V_ABI_VERSION 7
 #define N2V_MAX_PARTS 16
 
 /* error codes */
@@ -220,15 +220,33 @@ int n2v_walk(const n2v_graph_t* graph, const int32_t* start, int64_t n_start, in
              void* stream);
 
 /* The sampling constants n2v_walk derives from (p, q, graph flags); exposed so the host
- * replay in oracle/ and the roofline calculator use exactly the same numbers. */
+ * replay in oracle/ and the roofline calculator use exactly the same numbers.
+ *
+ * Mode 3 (mixture sampler).  On a unit-weight symmetric simple graph with q > 1 the reference's
+ * law at (prev t, cur v) (randomwalk.py:223-230), divided by 1/q, is
+ *     alpha(x) * q = 1  +  (q - 1) * [x in N(t) and N(v)]  +  (q/p - 1) * [x == t]        (x in N(v))
+ * i.e. a mixture of  (a) "bulk": x uniform on N(v), mass deg(v), always accepted (x == t only
+ * with probability min(1, q/p));  (b) "common neighbours": mass |N(t) & N(v)| * (q - 1), drawn by
+ * proposing x uniformly from the SMALLER of N(t), N(v) under the envelope mass
+ * min(deg t, deg v) * (q - 1) and accepting iff x is in the other set (one hash-bucket gather)
+ * and x != t;  (c) "return": mass max(0, q/p - 1), x = t.  One Philox draw picks the component
+ * with the fp32 thresholds below; a failed (b) proposal rejects the whole trial.  Proposals are
+ * the same 32-byte arc-record gathers as in the other modes, so an accepted x arrives with its
+ * adjacency header.  Compared with proposing from N(v) only this needs fewer trials whenever
+ * deg(t) < deg(v) and no membership test at all for bulk trials.
+ *     fo = fmul(float(min(dv, dt)), mix_qm1); tot = fadd(fadd(float(dv), fo), fold_gain);
+ *     thr_ret = rz(fmul(fdiv(fold_gain, tot), 2^32));
+ *     thr_out = sat(rz(fmul(fadd(fdiv(fold_gain, tot), fdiv(fo, tot)), 2^32)))      (all fp32, rn)
+ *     u32 < thr_ret: return;  u32 < thr_out: common-neighbour proposal;  else bulk. */
 typedef struct n2v_walk_consts {
   uint64_t t_ret;   /* accept x == prev      iff u32 < t_ret   (values in [0, 2^32]) */
   uint64_t t_nbr;   /* accept x in N_out(prev) iff u32 < t_nbr */
   uint64_t t_far;   /* accept otherwise      iff u32 < t_far */
-  float fold_gain;  /* e' = max(0, 1/p - cap) / cap; 0 = return-edge fold off */
-  int32_t fold_mode;/* 0 off, 1 unit-weight symmetric simple graph (rho = 1/deg), 2 general (per-arc ratios) */
+  float fold_gain;  /* modes 1/2: e' = max(0, 1/p - cap) / cap; mode 3: max(0, q/p - 1); 0 = return fold off */
+  int32_t fold_mode;/* 0 off, 1 unit-weight symmetric simple graph (rho = 1/deg), 2 general (per-arc ratios),
+                     * 3 "mixture" (unit-weight symmetric simple graph AND q > 1), see below */
   int32_t max_trials;
-  int32_t reserved;
+  float mix_qm1;    /* mode 3: q - 1 */
 } n2v_walk_consts_t;
 int n2v_walk_consts(double return_param, double inout_param, uint32_t graph_flags, int has_ratio,
                     n2v_walk_consts_t* out_host);
@@ -240,6 +258,20 @@ int n2v_walk_consts(double return_param, double inout_param, uint32_t graph_flag
  * returning through the fold, e*rev / (1 + e*rev), needs one 8-byte gather per step and no
  * search.  Single-part graphs; ratio_out: [n_arcs][2] fp32.  Run after n2v_alias_build. */
 int n2v_ratio_build(const n2v_graph_t* graph, float* ratio_out, void* stream);
+
+/* ---- K6: first-occurrence positions (graph indexer: name -> id remap, undirected dedupe) ----
+ * Replaces the two order-sensitive pandas steps of index_graph_pandas (indexer.py:9-49):
+ *   vertex id of a name = POSITION of its first occurrence in the concatenation
+ *   [all src..., all dst...] (:26-35, append + drop_duplicates + reset_index: ids are sparse,
+ *   up to 2E - 1), and the undirected expansion keeps the first occurrence of every
+ *   (src, dst, weight) triple in frame order (:45-48).
+ * first_out[i] = min { j : key[j] == key[i] } for rows keyed by 1-3 int64 columns (key1 / key2
+ * may be NULL; a weight column is passed as its IEEE bit pattern).  No sort: an open-addressing
+ * table of row positions, `n_slots` = n2v_first_occurrence_slots(n_rows) u32 entries of caller
+ * scratch.  n_rows < 2^32 - 1.  Row i is a first occurrence iff first_out[i] == i. */
+int64_t n2v_first_occurrence_slots(int64_t n_rows);
+int n2v_first_occurrence(const int64_t* key0, const int64_t* key1, const int64_t* key2, int64_t n_rows,
+                         uint32_t* table, int64_t n_slots, int64_t* first_out, void* stream);
 
 /* ---- K5: hotspot trimming, bit-exact with the reference's sampler ------------------------
  * Replaces trim_hotspot_vertices (randomwalk.py:238-262): a vertex with more than `cap` out-arcs

@@ -8,7 +8,7 @@ import os
 
 from . import build as _build
 
-N2V_ABI_VERSION = 6          # include/n2v_b200.h
+N2V_ABI_VERSION = 7          # include/n2v_b200.h
 N2V_MAX_PARTS = 16
 OK, ERR_INVALID, ERR_CUDA, ERR_SCRATCH, ERR_ZERO_WEIGHT = 0, 1, 2, 3, 4
 SUM_MODE = {"naive": 0, "neumaier": 1}
@@ -28,7 +28,7 @@ class Graph(C.Structure):
 class WalkConsts(C.Structure):
     _fields_ = [("t_ret", C.c_uint64), ("t_nbr", C.c_uint64), ("t_far", C.c_uint64),
                 ("fold_gain", C.c_float), ("fold_mode", C.c_int32), ("max_trials", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("mix_qm1", C.c_float)]
 
 
 class SgnsParams(C.Structure):
@@ -65,6 +65,8 @@ _SIGNATURES = {
     "n2v_walk_consts": (C.c_int, [C.c_double, C.c_double, C.c_uint32, C.c_int, C.POINTER(WalkConsts)]),
     "n2v_ratio_build": (C.c_int, [C.POINTER(Graph), _P, _P]),
     "n2v_trim_sample": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_uint32, _P, _P, _P]),
+    "n2v_first_occurrence_slots": (C.c_int64, [C.c_int64]),
+    "n2v_first_occurrence": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_int64, _P, _P]),
     "n2v_vocab_count": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
     "n2v_sgns_prepare": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_double, C.c_double, _P, _P, _P,
                                    C.POINTER(C.c_int64), _P]),

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(CSRC, "libn2v_b200.so")
-SOURCES = ["abi.cu", "peer_mem.cu", "csr_build.cu", "hash_build.cu", "alias_build.cu", "trim.cu", "walk.cu", "vocab.cu", "sgns.cu", "sgns_shared.cu"]
+SOURCES = ["abi.cu", "peer_mem.cu", "csr_build.cu", "hash_build.cu", "alias_build.cu", "trim.cu", "index.cu", "walk.cu", "vocab.cu", "sgns.cu", "sgns_shared.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--extended-lambda", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",

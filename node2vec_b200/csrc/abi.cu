@@ -44,6 +44,18 @@ extern "C" int n2v_walk_consts(double return_param, double inout_param, uint32_t
   const uint32_t need = N2V_GRAPH_UNIT_WEIGHT | N2V_GRAPH_SYMMETRIC | N2V_GRAPH_SIMPLE;
   double cap = iq > 1.0 ? iq : 1.0;
   memset(out, 0, sizeof(*out));
+  if ((graph_flags & need) == need && inout_param > 1.0) {
+    // mixture sampler (mode 3, see n2v_b200.h): bulk + common-neighbour + return components
+    const double g = inout_param / return_param - 1.0;
+    out->fold_mode = 3;
+    out->fold_gain = static_cast<float>(g > 0.0 ? g : 0.0);
+    out->mix_qm1 = static_cast<float>(inout_param - 1.0);
+    const double a_ret = inout_param / return_param;      // bulk acceptance of x == prev: min(1, (1/p) / (1/q))
+    out->t_ret = accept_threshold(a_ret < 1.0 ? a_ret : 1.0);
+    out->t_nbr = out->t_far = 4294967296ull;
+    out->max_trials = 256;
+    return N2V_OK;
+  }
   if (ip > cap) {
     if ((graph_flags & need) == need) {
       out->fold_mode = 1;

@@ -56,6 +56,7 @@ struct WalkArgs {
   // accept iff u32 <= *_m1
   uint32_t ret_m1, nbr_m1, far_m1, lo_m1, hi_m1;
   float fold_gain;
+  float mix_qm1;
   int32_t max_trials;
   double inv_p, inv_q;
 };
@@ -129,7 +130,20 @@ __device__ __forceinline__ uint32_t fold_threshold_ratio(float gain, float rev) 
   return pr >= 1.0f ? 0xFFFFFFFFu : __float2uint_rz(__fmul_rn(pr, 4294967296.0f));
 }
 
-// FOLD: 0 = off, 1 = unit-weight symmetric simple graph, 2 = general (per-arc {fwd, rev} ratios)
+// mixture sampler (mode 3, n2v_b200.h): component thresholds at (prev t, cur v) from the two degrees
+__device__ __forceinline__ void mix_thresholds(float gain_r, float qm1, uint32_t deg_v, uint32_t deg_t,
+                                               uint32_t& thr_ret, uint32_t& thr_out) {
+  const float fo = __fmul_rn(static_cast<float>(min(deg_v, deg_t)), qm1);
+  const float tot = __fadd_rn(__fadd_rn(static_cast<float>(deg_v), fo), gain_r);
+  const float pr = __fdiv_rn(gain_r, tot);
+  const float po = __fdiv_rn(fo, tot);
+  thr_ret = __float2uint_rz(__fmul_rn(pr, 4294967296.0f));
+  const float s = __fmul_rn(__fadd_rn(pr, po), 4294967296.0f);
+  thr_out = s >= 4294967296.0f ? 0xFFFFFFFFu : __float2uint_rz(s);
+}
+
+// FOLD: 0 = off, 1 = unit-weight symmetric simple graph, 2 = general (per-arc {fwd, rev} ratios),
+//       3 = mixture sampler (unit-weight symmetric simple graph, q > 1)
 template <int FOLD, bool MULTI, bool STATS>
 __global__ void __launch_bounds__(kBlock, kBlocksPerSm)
 walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkArgs A) {
@@ -143,7 +157,7 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
   // walker state (offsets are 32-bit: a part holds < 2^32 arcs / buckets)
   int32_t t = -1, v = 0, pos = 0;
   uint32_t deg_t = 0, deg_v = 0, base_v = 0, base_t = 0;
-  uint32_t trial = 0, thr_out = 0, wid_lo = 0, wid_hi = 0;
+  uint32_t trial = 0, thr_out = 0, thr_ret = 0, wid_lo = 0, wid_hi = 0;
   uint32_t part_v = 0, part_t = 0;
   float r_fwd = 0.f, r_rev = 0.f;   // FOLD == 2: ratios of the arc that brought the walker to v
   bool active = false;
@@ -223,7 +237,37 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
     int32_t x;
     uint32_t base_x, deg_x;   // adjacency header of x, delivered with the proposal
     uint32_t arc_index = 0xFFFFFFFFu;   // part-local index of the arc taken (FOLD == 2)
-    if (FOLD != 0 && !first && rnd.x < thr_out) {
+    if (FOLD == 3 && !first) {
+      if (rnd.x < thr_ret) {               // return component
+        x = t;
+        base_x = base_t;
+        deg_x = deg_t;
+        accept = true;
+        if (STATS) ++c_fold;
+      } else {
+        const bool common = rnd.x < thr_out;          // common-neighbour proposal, else bulk
+        const bool from_t = common && deg_t < deg_v;  // propose from the smaller adjacency
+        const uint32_t k = __umulhi(rnd.y, from_t ? deg_t : deg_v);
+        const n2v::Int8 arc = n2v::load_sector(g.parts[MULTI ? (from_t ? part_t : part_v) : 0].arcs +
+                                               (from_t ? base_t : base_v) + k);
+        const bool self = rnd.z < static_cast<uint32_t>(arc.a[0]);
+        x = self ? arc.a[1] : arc.a[2];
+        base_x = static_cast<uint32_t>(self ? arc.a[4] : arc.a[6]);
+        deg_x = static_cast<uint32_t>(self ? arc.a[5] : arc.a[7]);
+        if (STATS) ++c_trials;
+        if (!common) {
+          accept = (x != t) || (rnd.w <= A.ret_m1);
+        } else {
+          if (STATS) ++c_search;
+          uint32_t probes = 0;
+          const bool in = from_t
+              ? member(g.parts[MULTI ? part_v : 0].hash, n2v_hash_base(base_v, local_of(v, part_v)), deg_v, x, probes)
+              : member(g.parts[MULTI ? part_t : 0].hash, n2v_hash_base(base_t, local_of(t, part_t)), deg_t, x, probes);
+          if (STATS) c_probes += probes;
+          accept = in && x != t;
+        }
+      }
+    } else if (FOLD != 0 && FOLD != 3 && !first && rnd.x < thr_out) {
       x = t;
       base_x = base_t;
       deg_x = deg_t;
@@ -295,6 +339,7 @@ walk_kernel(const __grid_constant__ n2v_graph_t g, const __grid_constant__ WalkA
     if ((pos & (kStage - 1)) == kStage - 1) flush_chunk(pos >> 3);
     if (FOLD == 1) thr_out = fold_threshold(A.fold_gain, deg_v);
     if (FOLD == 2) thr_out = fold_threshold_ratio(A.fold_gain, r_rev);
+    if (FOLD == 3) mix_thresholds(A.fold_gain, A.mix_qm1, deg_v, deg_t, thr_ret, thr_out);
   }
 
   if (STATS) {  // one atomic per counter per warp
@@ -347,6 +392,7 @@ extern "C" int n2v_walk(const n2v_graph_t* graph, const int32_t* start, int64_t 
   A.lo_m1 = A.nbr_m1 < A.far_m1 ? A.nbr_m1 : A.far_m1;
   A.hi_m1 = A.nbr_m1 < A.far_m1 ? A.far_m1 : A.nbr_m1;
   A.fold_gain = C.fold_gain;
+  A.mix_qm1 = C.mix_qm1;
   A.max_trials = C.max_trials;
   A.inv_p = 1.0 / return_param;
   A.inv_q = 1.0 / inout_param;
@@ -375,7 +421,14 @@ extern "C" int n2v_walk(const n2v_graph_t* graph, const int32_t* start, int64_t 
       case 6: N2V_LAUNCH_WALK(1, true, false); break;
       case 7: N2V_LAUNCH_WALK(1, true, true); break;
       case 8: N2V_LAUNCH_WALK(2, false, false); break;
-      default: N2V_LAUNCH_WALK(2, false, true); break;   // general fold is single-part only
+      case 9: N2V_LAUNCH_WALK(2, false, true); break;    // general fold is single-part only
+      case 12: N2V_LAUNCH_WALK(3, false, false); break;
+      case 13: N2V_LAUNCH_WALK(3, false, true); break;
+      case 14: N2V_LAUNCH_WALK(3, true, false); break;
+      case 15: N2V_LAUNCH_WALK(3, true, true); break;
+      default:
+        n2v::set_error("n2v_walk: fold mode %d is not available on a %d-part graph", fold, graph->n_parts);
+        return N2V_ERR_INVALID;
     }
 #undef N2V_LAUNCH_WALK
     N2V_LAUNCH_OK();

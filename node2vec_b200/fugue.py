@@ -140,33 +140,48 @@ def trim_index(
     directed: bool = True,
     max_out_deg: int = 0,
     random_seed: Optional[int] = None,
+    *,
+    dense_ids: bool = False,
 ) -> Tuple[Frame, Optional[Frame]]:
     """Validate, trim hotspot vertices, index.  Same contract as the reference
     (fugue.py:24-77): ``max_out_deg <= 0`` means 100000 (randomwalk.py:254-255);
-    ``indexed=True`` returns the trimmed frame untouched and ``None``."""
+    ``indexed=True`` returns the trimmed frame untouched and ``None``.
+    Frames whose ``src`` / ``dst`` are integer names are trimmed, indexed and (``directed=False``)
+    mirrored ON THE DEVICE when a GPU is present -- K5 / K6, one H2D of the columns in, the frames the
+    reference returns out, row for row; string names are first replaced by their rank among the sorted
+    distinct names on the host (one pass), the row-level work is the same device path.
+    Tuples of device tensors ``(src, dst[, weight])`` (integer names) never leave the GPU and return
+    ``((src, dst, weight), (vertex_id, vertex_name))`` tensors.  Keyword-only ``dense_ids=True`` numbers
+    vertices 0..V-1 in first-occurrence order instead of the reference's sparse positions."""
     logging.info("trim_index(): start validating, trimming, and indexing ...")
     if isinstance(df_graph, (tuple, list)) and len(df_graph) in (2, 3) and isinstance(df_graph[0], torch.Tensor):
-        # integer-id arc tensors (graphs too large for pandas): device-side trimming / symmetrising
-        from .preprocess import symmetrise_device, trim_hotspots_device
-        if indexed is not True:
-            raise ValueError("tensor inputs must already be indexed (integer vertex ids): pass indexed=True")
+        # integer vertex names / ids as device tensors (graphs too large for pandas): everything stays on the GPU.
+        # The reference's order: partition by src + trim (fugue.py:57-67), then index (first-occurrence ids,
+        # indexer.py:26-43), then expand to both directions (indexer.py:45-48).
+        from .preprocess import index_graph_device, symmetrise_device, trim_partitioned
         src, dst = df_graph[0], df_graph[1]
         w = df_graph[2] if len(df_graph) == 3 else None
-        # the reference's order: trim the arcs as listed (fugue.py:57-67), THEN expand to both
-        # directions (indexer.py:45-48) -- so a trimmed hub keeps its mirrored in-arcs and the
-        # graph stays symmetric.  (For frames the reference returns before the expansion when
-        # indexed=True, fugue.py:70-71; tensors are always indexed, so `directed` is honoured
-        # here -- INTEGRATION.md notes the difference.)
-        src, dst, w = trim_hotspots_device(src, dst, w, max_out_deg, random_seed)
-        if directed is not True:
-            src, dst, w = symmetrise_device(src, dst, w)
-        return ((src, dst) if w is None else (src, dst, w)), None
+        src, dst, w = trim_partitioned(src, dst, w, max_out_deg, random_seed)
+        if indexed is True:
+            # frames return here (fugue.py:70-71); tensors are always indexed, so `directed` is honoured for
+            # them: trimmed first, mirrored afterwards, a trimmed hub keeps its mirrored in-arcs and the graph
+            # stays symmetric (INTEGRATION.md notes the difference)
+            if directed is not True:
+                src, dst, w = symmetrise_device(src, dst, w)
+            return ((src, dst) if w is None else (src, dst, w)), None
+        s, d, wt, vid, vname = index_graph_device(src, dst, w, directed, dense_ids=dense_ids)
+        return (s, d, wt), (vid, vname)
     cols = _columns(df_graph)
     if "src" not in cols or "dst" not in cols:
         raise ValueError(f"Input graph NOT in the right format: {cols}")
     _reject_spark(compute_engine)
     df = _to_pandas(df_graph)
+    if indexed is not True and torch.cuda.is_available() and set(df.columns) <= {"src", "dst", "weight"}:
+        res = _trim_index_frame_on_device(df, directed, max_out_deg, random_seed)
+        if res is not None:
+            return res
     cap = max_out_deg if max_out_deg > 0 else MAX_OUT_DEGREES
+    # host path (no GPU, or columns / name types the device path does not take):
     # partition(by=["src"]) + trim_hotspot_vertices: groups come out in key order, rows in
     # input order, an oversize group is replaced by DataFrame.sample(n=cap, random_state=seed)
     df = df.sort_values("src", kind="stable")
@@ -184,6 +199,48 @@ def trim_index(
         return Frame(df), None
     df_res, name_id = index_graph_pandas(df, directed)
     return Frame(df_res.reset_index(drop=True)), Frame(name_id)
+
+
+def _trim_index_frame_on_device(df: pd.DataFrame, directed, max_out_deg, random_seed):
+    """trim_index for a pandas frame with the row-level work on the GPU (K5 trimming, K6 indexing and
+    de-duplication): one H2D of the columns, the reference's two frames back.  Integer names go to
+    the device as they are; other names (strings) are replaced on the host by their rank among the
+    sorted distinct names -- equality- and order-preserving, so partition order, first-occurrence
+    ids and the undirected expansion are unchanged -- and mapped back in the name table.
+    Returns None when the names cannot be ranked (mixed types): the caller falls back to pandas."""
+    from .preprocess import index_graph_device, trim_partitioned
+    src, dst = df["src"].to_numpy(), df["dst"].to_numpy()
+    uniques = None
+    if src.dtype.kind in "iu" and dst.dtype.kind in "iu" and src.dtype.itemsize <= 8 and dst.dtype.itemsize <= 8 \
+            and src.dtype != np.uint64 and dst.dtype != np.uint64:
+        s_key, d_key = src.astype(np.int64), dst.astype(np.int64)
+        name_dtype = src.dtype if src.dtype == dst.dtype else object
+    else:
+        try:
+            codes, uniques = pd.factorize(np.concatenate([src.astype(object), dst.astype(object)]), sort=True)
+        except TypeError:
+            return None
+        if (codes < 0).any():
+            return None                                   # missing names: leave them to pandas' semantics
+        s_key, d_key = codes[: len(src)].astype(np.int64), codes[len(src):].astype(np.int64)
+        name_dtype = object
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ts, td = torch.as_tensor(s_key, device=dev), torch.as_tensor(d_key, device=dev)
+    tw = None
+    if "weight" in df.columns:
+        tw = torch.as_tensor(df["weight"].to_numpy().astype(np.float64), device=dev)
+    else:
+        df["weight"] = 1.0                                # the reference adds the column to the caller's frame too
+    ts, td, tw = trim_partitioned(ts, td, tw, max_out_deg, random_seed)
+    s, d, w, vid, vname = index_graph_device(ts, td, tw, directed)
+    vname = vname.cpu().numpy()
+    names = uniques[vname] if uniques is not None else (vname.astype(name_dtype) if name_dtype is not object
+                                                        else vname.astype(object))
+    df_edge = pd.DataFrame({"src": s.cpu().numpy(), "dst": d.cpu().numpy(), "weight": w.cpu().numpy()})
+    name_id = pd.DataFrame({"vertex_id": vid.cpu().numpy(), "vertex_name": names})
+    logging.info(f"Num of indexed vertices: {len(name_id)}")
+    logging.info(f"Num of indexed edges: {len(df_edge)}")
+    return Frame(df_edge), Frame(name_id)
 
 
 def _graph_arrays(df_graph):

@@ -2,8 +2,11 @@
 ``trim_index`` (reference fugue.py:24-77) that precedes the hot path -- hotspot trimming
 (randomwalk.py:238-262) and the undirected expansion of the indexer (indexer.py:45-48).
 
-Data-preparation built from torch primitives (sort / unique / bincount on the GPU) plus K5
-``n2v_trim_sample``; not part of the measured hot path.  With a ``seed`` the kept arcs and their
+Data preparation: the reference's partition step is one stable device sort by source vertex; the
+two order-sensitive pandas steps of its indexer -- first-occurrence vertex ids and the
+first-occurrence de-duplication of the undirected expansion -- run in K6 ``n2v_first_occurrence``
+(a sort-free position hash table, ``csrc/index.cu``); trimming is K5 ``n2v_trim_sample``.  Not part
+of the measured hot path.  With a ``seed`` the kept arcs and their
 order are bit-identical to the reference's pandas path (``DataFrame.sample(n, random_state=seed)``
 = numpy's legacy ``RandomState(seed).permutation(deg)[:n]``, re-seeded per vertex; the kernel runs
 MT19937 and the Fisher-Yates shuffle on the device).  Without a seed the reference draws from the
@@ -81,19 +84,111 @@ def _trim_exact(src, dst, weight, s, deg, cap: int, seed: int):
 
 def symmetrise_device(src: torch.Tensor, dst: torch.Tensor, weight: Optional[torch.Tensor] = None
                       ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
-    """indexer.py:45-48: append the reversed arcs, drop exact duplicate (src, dst, weight) triples
-    (first occurrence kept; output ordered by (src, dst), which the CSR build would do anyway)."""
-    s = torch.cat([src, dst]).long()
-    d = torch.cat([dst, src]).long()
+    """indexer.py:45-48 on integer ids: append the reversed arcs, keep the first occurrence of every
+    (src, dst, weight) triple in frame order (K6, no sort)."""
+    s = torch.cat([src, dst]).to(torch.int64)
+    d = torch.cat([dst, src]).to(torch.int64)
+    n = int(s.numel())
+    pos = torch.arange(n, device=s.device)
     if weight is None:
-        key = torch.unique((s << 32) | d)
-        return (key >> 32).to(src.dtype), (key & 0xFFFFFFFF).to(dst.dtype), None
+        keep = first_occurrence(s, d) == pos
+        return s[keep].to(src.dtype), d[keep].to(dst.dtype), None
     w = torch.cat([weight, weight])
-    wbits = w.double().view(torch.int64)
-    order = torch.argsort(wbits, stable=True)
-    order = order[torch.argsort(((s << 32) | d)[order], stable=True)]
-    k, wb = ((s << 32) | d)[order], wbits[order]
-    first = torch.ones_like(k, dtype=torch.bool)
-    first[1:] = (k[1:] != k[:-1]) | (wb[1:] != wb[:-1])
-    sel = order[first]
-    return s[sel].to(src.dtype), d[sel].to(dst.dtype), w[sel]
+    keep = first_occurrence(s, d, _weight_key(w)) == pos
+    return s[keep].to(src.dtype), d[keep].to(dst.dtype), w[keep]
+
+
+# ======================================================================================
+# K6: the reference's graph indexer on the device (indexer.py:9-49)
+# ======================================================================================
+def first_occurrence(*cols: torch.Tensor) -> torch.Tensor:
+    """first[i] = the smallest j whose key (1-3 int64 columns) equals row i's.  No sort."""
+    lib = _lib.load()
+    if not 1 <= len(cols) <= 3:
+        raise ValueError("1 to 3 key columns")
+    cols = [c.contiguous() if c.dtype == torch.int64 else c.to(torch.int64).contiguous() for c in cols]
+    n, dev = int(cols[0].numel()), cols[0].device
+    out = torch.empty(n, dtype=torch.int64, device=dev)
+    if n == 0:
+        return out
+    n_slots = int(lib.n2v_first_occurrence_slots(n))
+    with torch.cuda.device(dev):
+        table = torch.empty(n_slots, dtype=torch.int32, device=dev)
+        ptrs = [_lib.ptr(c) for c in cols] + [None] * (3 - len(cols))
+        _lib.check(lib.n2v_first_occurrence(ptrs[0], ptrs[1], ptrs[2], n, _lib.ptr(table), n_slots, _lib.ptr(out),
+                                            _lib.current_stream_ptr()), "n2v_first_occurrence")
+    return out
+
+
+def _weight_key(w: torch.Tensor) -> torch.Tensor:
+    """IEEE bit pattern with pandas' equality: -0.0 == 0.0 and every NaN equals every NaN."""
+    w = w.double()
+    w = torch.where(w == 0, torch.zeros_like(w), w)
+    w = torch.where(torch.isnan(w), torch.full_like(w, float("nan")), w)
+    return w.contiguous().view(torch.int64)
+
+
+def index_graph_device(src_name: torch.Tensor, dst_name: torch.Tensor, weight: Optional[torch.Tensor] = None,
+                       directed: bool = True, dense_ids: bool = False):
+    """``index_graph_pandas`` (indexer.py:9-49) for integer vertex names, on the device, row for row:
+    vertex id = position of the name's first occurrence in [all src..., all dst...] (:26-35; sparse,
+    up to 2E - 1), arcs keep their order, weight defaults to 1.0 (fp64), and ``directed=False``
+    appends the reversed arcs and keeps the first occurrence of every (src, dst, weight) triple
+    (:45-48).  ``dense_ids=True`` numbers the vertices 0..V-1 in first-occurrence order instead
+    (compact tables for the walk / SGNS kernels; the name table maps back).
+    Returns (src_id, dst_id, weight, vertex_id, vertex_name), all device tensors."""
+    dev = src_name.device
+    e = int(src_name.numel())
+    names = torch.cat([src_name.to(torch.int64), dst_name.to(torch.int64)])
+    first = first_occurrence(names)
+    is_first = first == torch.arange(2 * e, device=dev)
+    vertex_pos = torch.nonzero(is_first).view(-1)            # ascending positions = first-occurrence order
+    vertex_name = names[vertex_pos]
+    if dense_ids:
+        rank = torch.cumsum(is_first.to(torch.int64), 0) - 1
+        ids = rank[first]
+        vertex_id = torch.arange(int(vertex_pos.numel()), device=dev)
+    else:
+        ids, vertex_id = first, vertex_pos
+    s, d = ids[:e], ids[e:]
+    w = torch.ones(e, dtype=torch.float64, device=dev) if weight is None else weight.to(torch.float64)
+    if directed is not True:
+        s2, d2, w2 = torch.cat([s, d]), torch.cat([d, s]), torch.cat([w, w])
+        keep = first_occurrence(s2, d2, _weight_key(w2)) == torch.arange(2 * e, device=dev)
+        s, d, w = s2[keep], d2[keep], w2[keep]               # boolean selection preserves frame order
+    return s, d, w, vertex_id, vertex_name
+
+
+def partition_by_src(src: torch.Tensor, dst: torch.Tensor, weight: Optional[torch.Tensor] = None):
+    """``partition(by=["src"])`` (fugue.py:57-60): rows grouped by source in ascending key order,
+    input order inside a group -- one stable device sort."""
+    order = torch.sort(src, stable=True).indices
+    return src[order], dst[order], (None if weight is None else weight[order])
+
+
+def trim_partitioned(src: torch.Tensor, dst: torch.Tensor, weight: Optional[torch.Tensor] = None,
+                     max_out_deg: int = 0, seed: Optional[int] = None):
+    """``partition(by=["src"]).transform(trim_hotspot_vertices)`` (fugue.py:57-67) for integer source
+    names of any range: rows come out grouped by ascending source, input order inside a group, an
+    oversize group replaced by its sample (seeded: the rows ``DataFrame.sample`` keeps, in its order)."""
+    src, dst, weight = partition_by_src(src, dst, weight)
+    if src.numel() == 0:
+        return src, dst, weight
+    head = torch.ones(src.numel(), dtype=torch.bool, device=src.device)
+    head[1:] = src[1:] != src[:-1]
+    group = torch.cumsum(head.to(torch.int64), 0) - 1          # dense rank of the source among the sorted sources
+    cap = max_out_deg if max_out_deg > 0 else MAX_OUT_DEGREES
+    deg = torch.bincount(group)
+    if int(deg.max()) <= cap:
+        return src, dst, weight
+    if seed is not None:
+        return _trim_exact(src, dst, weight, group, deg, cap, int(seed))
+    keep = torch.ones(src.numel(), dtype=torch.bool, device=src.device)
+    gen = torch.Generator(device=src.device)
+    gen.seed()
+    tag = torch.rand(src.numel(), device=src.device, generator=gen)
+    order = torch.sort(group.double() + tag * 0.999999, stable=True).indices      # random order inside each group
+    start = torch.cumsum(deg, 0) - deg
+    rank = torch.arange(src.numel(), device=src.device) - start[group[order]]
+    keep[order[rank >= cap]] = False
+    return src[keep], dst[keep], (None if weight is None else weight[keep])

@@ -29,7 +29,7 @@ def build(force: bool = False) -> str:
 class WalkConsts(C.Structure):
     _fields_ = [("t_ret", C.c_uint64), ("t_nbr", C.c_uint64), ("t_far", C.c_uint64),
                 ("fold_gain", C.c_float), ("fold_mode", C.c_int32), ("max_trials", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("mix_qm1", C.c_float)]
 
 
 def _ptr(a, t):

@@ -295,7 +295,7 @@ typedef struct orc_walk_consts {
   float fold_gain;
   int32_t fold_mode;
   int32_t max_trials;
-  int32_t reserved;
+  float mix_qm1; /* mode 3: q - 1 */
 } orc_walk_consts;
 
 static uint64_t accept_thr(double a) {
@@ -313,6 +313,17 @@ int orc_walk_consts_for(double p, double q, uint32_t graph_flags, int has_ratio,
   const double ip = 1.0 / p, iq = 1.0 / q;
   double cap = iq > 1.0 ? iq : 1.0;
   memset(c, 0, sizeof(*c));
+  if ((graph_flags & 7u) == 7u && q > 1.0) { /* mixture sampler (include/n2v_b200.h, mode 3) */
+    const double g = q / p - 1.0;
+    const double a_ret = q / p;
+    c->fold_mode = 3;
+    c->fold_gain = (float)(g > 0.0 ? g : 0.0);
+    c->mix_qm1 = (float)(q - 1.0);
+    c->t_ret = accept_thr(a_ret < 1.0 ? a_ret : 1.0);
+    c->t_nbr = c->t_far = 4294967296ull;
+    c->max_trials = 256;
+    return 0;
+  }
   if (ip > cap) {
     if ((graph_flags & 7u) == 7u) { c->fold_mode = 1; c->fold_gain = (float)((ip - cap) / cap); }
     else if (has_ratio) { c->fold_mode = 2; c->fold_gain = (float)((ip - cap) / cap); }
@@ -391,8 +402,16 @@ int orc_replay_walk(const uint64_t* base, const uint32_t* deg, const uint32_t* a
     for (int32_t pos = 0; pos < walk_length; ++pos) {
       const uint32_t dv = deg[v];
       if (dv == 0) { ok = 0; ++st[6]; break; }
-      uint32_t thr_out = 0;
-      if (c->fold_mode == 1 && pos > 0) {
+      uint32_t thr_out = 0, thr_ret = 0;
+      if (c->fold_mode == 3 && pos > 0) {
+        const uint32_t dt = deg[t];
+        const float fo = (float)(dv < dt ? dv : dt) * c->mix_qm1;
+        const float tot = ((float)dv + fo) + c->fold_gain;
+        const float pr = c->fold_gain / tot, po = fo / tot;
+        const float s = (pr + po) * 4294967296.0f;
+        thr_ret = (uint32_t)(pr * 4294967296.0f);
+        thr_out = s >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)s;
+      } else if (c->fold_mode == 1 && pos > 0) {
         const float pr = c->fold_gain / ((float)dv + c->fold_gain);
         thr_out = pr >= 1.0f ? 0xFFFFFFFFu : (uint32_t)(pr * 4294967296.0f);
       } else if (c->fold_mode == 2 && pos > 0) {
@@ -407,6 +426,24 @@ int orc_replay_walk(const uint64_t* base, const uint32_t* deg, const uint32_t* a
         const uint32_t ctr[4] = {(uint32_t)walk_id, (uint32_t)(walk_id >> 32), (uint32_t)pos, trial};
         uint32_t r[4];
         philox4x32_10(k0, k1, ctr, r);
+        if (c->fold_mode == 3 && pos > 0) {
+          if (r[0] < thr_ret) { x = t; accepted = 1; arc_index = -1; ++st[4]; break; }
+          const int common = r[0] < thr_out;
+          const int from_t = common && deg[t] < dv;
+          const int32_t side = from_t ? t : v;
+          const uint64_t e = base[side] + (uint64_t)(((uint64_t)r[1] * deg[side]) >> 32);
+          const int self = r[2] < arc_thr[e];
+          x = self ? arc_dst[e] : arc_alias_dst[e];
+          ++st[1];
+          if (!common) accepted = (x != t) || (r[3] <= ret_m1);
+          else {
+            const int32_t other = from_t ? v : t;
+            ++st[3];
+            accepted = member_probe(col + base[other], deg[other], x, &st[2]) && x != t;
+          }
+          if (accepted) break;
+          continue;
+        }
         if (c->fold_mode != 0 && pos > 0 && r[0] < thr_out) { x = t; accepted = 1; arc_index = -1; ++st[4]; break; }
         const uint64_t e = base[v] + (uint64_t)(((uint64_t)r[1] * dv) >> 32);
         const int self = r[2] < arc_thr[e];

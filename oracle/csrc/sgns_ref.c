@@ -58,12 +58,22 @@ int64_t orc_sgns_vocab(const int64_t* counts, int64_t V, int64_t min_count, doub
     keep_int[v] = 0;
     if (counts[v] >= min_count && counts[v] > 0) { order[n++] = (int32_t)v; retain_total += counts[v]; }
   }
-  /* stable sort by descending count (insertion into buckets would do; V is small in tests) */
-  for (int64_t i = 1; i < n; ++i) {
-    const int32_t x = order[i];
-    int64_t j = i - 1;
-    while (j >= 0 && counts[order[j]] < counts[x]) { order[j + 1] = order[j]; --j; }
-    order[j + 1] = x;
+  /* stable sort by descending count: bottom-up merge sort (ties keep id order), O(n log n) */
+  if (n > 1) {
+    int32_t* tmp = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    int32_t *a = order, *b = tmp;
+    for (int64_t width = 1; width < n; width *= 2) {
+      for (int64_t lo = 0; lo < n; lo += 2 * width) {
+        const int64_t mid = lo + width < n ? lo + width : n, hi = lo + 2 * width < n ? lo + 2 * width : n;
+        int64_t i = lo, j = mid, k = lo;
+        while (i < mid && j < hi) b[k++] = (counts[a[j]] > counts[a[i]]) ? a[j++] : a[i++];
+        while (i < mid) b[k++] = a[i++];
+        while (j < hi) b[k++] = a[j++];
+      }
+      int32_t* t = a; a = b; b = t;
+    }
+    if (a != order) memcpy(order, a, sizeof(int32_t) * (size_t)n);
+    free(tmp);
   }
   double threshold;
   if (sample == 0.0) threshold = (double)retain_total;

@@ -33,7 +33,7 @@ def test_header_symbols_exported(lib):
 
 def test_abi_version_and_struct_sizes(lib):
     from node2vec_b200 import _lib
-    assert lib.n2v_abi_version() == 6
+    assert lib.n2v_abi_version() == 7
     assert C.sizeof(_lib.GraphPart) == 48
     assert C.sizeof(_lib.Graph) == 8 + 8 + 4 + 4 + 8 + 48 * 16
     assert C.sizeof(_lib.WalkConsts) == 40
@@ -62,12 +62,18 @@ def test_walk_consts_host_only(lib):
             a, b = graph.walk_consts(p, q, flags, ratio), clib.walk_consts(p, q, flags, ratio)
             assert (a.t_ret, a.t_nbr, a.t_far, a.fold_mode, a.max_trials) == \
                    (b.t_ret, b.t_nbr, b.t_far, b.fold_mode, b.max_trials)
-            assert a.fold_gain == b.fold_gain
+            assert a.fold_gain == b.fold_gain and a.mix_qm1 == b.mix_qm1
             assert 1 <= a.t_ret <= 2 ** 32 and 1 <= a.t_nbr <= 2 ** 32 and 1 <= a.t_far <= 2 ** 32
     c = graph.walk_consts(1.0, 1.0, 0)
     assert c.t_ret == c.t_nbr == c.t_far == 2 ** 32 and c.fold_mode == 0
-    c = graph.walk_consts(0.25, 4.0, 7)                     # fold: envelope stays at max(1, 1/q) = 1
-    assert c.fold_mode == 1 and c.t_nbr == 2 ** 32 and c.t_far == 2 ** 30 and abs(c.fold_gain - 3.0) < 1e-6
+    c = graph.walk_consts(0.25, 1.0, 7)                     # fold: envelope stays at max(1, 1/q) = 1
+    assert c.fold_mode == 1 and c.t_nbr == 2 ** 32 and c.t_far == 2 ** 32 and abs(c.fold_gain - 3.0) < 1e-6
+    c = graph.walk_consts(0.25, 4.0, 7)                     # unit symmetric simple graph, q > 1: mixture sampler
+    assert c.fold_mode == 3 and c.t_ret == 2 ** 32 and c.fold_gain == 15.0 and c.mix_qm1 == 3.0
+    c = graph.walk_consts(8.0, 2.0, 7)                      # p > q > 1: no return excess, x == prev thinned in the bulk
+    assert c.fold_mode == 3 and c.t_ret == 2 ** 30 and c.fold_gain == 0.0 and c.mix_qm1 == 1.0
+    c = graph.walk_consts(0.25, 4.0, 5)                     # not symmetric: no mixture
+    assert c.fold_mode == 0
     c = graph.walk_consts(0.25, 4.0, 0)                     # no fold possible: envelope 1/p = 4
     assert c.fold_mode == 0 and c.t_ret == 2 ** 32 and c.t_nbr == 2 ** 30 and c.t_far == 2 ** 28
     c = graph.walk_consts(0.25, 4.0, 0, True)               # general fold through per-arc ratios

@@ -114,6 +114,7 @@ def _second_order_counts(walks, alive, pos):
     (1.0, 1.0, True, False, False), (1.0, 0.5, False, True, False), (0.25, 4.0, False, True, False),
     (4.0, 0.25, True, True, False), (0.25, 4.0, True, False, False), (0.5, 2.0, False, False, False),
     (0.25, 4.0, True, False, True), (0.2, 1.0, True, True, True), (0.5, 2.0, False, False, True),
+    (4.0, 2.0, False, True, False), (1.0, 3.0, False, True, False), (0.1, 1.5, False, True, False),
 ])
 def test_replay_draws_from_reference_law(p, q, weighted, sym, use_ratio):
     rng = np.random.default_rng(11)
@@ -131,7 +132,8 @@ def test_replay_draws_from_reference_law(p, q, weighted, sym, use_ratio):
     w = [wmap[(min(a, b), max(a, b)) if sym else (a, b)] for a, b in pairs]
     row_ptr, col, ws, thr, adst, aalias, flags = _replay_setup(src, dst, w, n)
     consts = clib.walk_consts(p, q, flags)
-    assert (consts.fold_mode == 1) == (p < min(1.0, q) and not weighted and sym)
+    plain = not weighted and sym                   # unit-weight symmetric simple graph
+    assert consts.fold_mode == (3 if (plain and q > 1.0) else 1 if (plain and p < min(1.0, q)) else 0)
     starts = np.flatnonzero(np.diff(row_ptr) > 0).astype(np.int32)
     ratio = alias_idx = None
     if use_ratio:
