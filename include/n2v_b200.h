@@ -259,6 +259,16 @@ int n2v_walk_consts(double return_param, double inout_param, uint32_t graph_flag
  * search.  Single-part graphs; ratio_out: [n_arcs][2] fp32.  Run after n2v_alias_build. */
 int n2v_ratio_build(const n2v_graph_t* graph, float* ratio_out, void* stream);
 
+/* ---- device tuning: L2 fetch granularity ------------------------------------------------
+ * The walk is a stream of random 32-byte gathers (one arc record / one hash bucket each).  With the
+ * driver's default L2 fetch granularity a missing sector pulls its whole 128-byte line from HBM:
+ * ncu on the RMAT-20 walk shows 3.4 DRAM sectors per requested sector (profiles/).  Setting
+ * cudaLimitMaxL2FetchGranularity to 32 makes L2 fetch what was asked for.  The limit is a property
+ * of the CUDA context (all kernels of the process on this device), a performance hint only.
+ * bytes: 32, 64 or 128.  get returns the current limit (or -1 on error). */
+int n2v_set_l2_fetch_granularity(int bytes);
+int n2v_get_l2_fetch_granularity(void);
+
 /* ---- K6: first-occurrence positions (graph indexer: name -> id remap, undirected dedupe) ----
  * Replaces the two order-sensitive pandas steps of index_graph_pandas (indexer.py:9-49):
  *   vertex id of a name = POSITION of its first occurrence in the concatenation

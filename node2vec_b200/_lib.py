@@ -65,6 +65,8 @@ _SIGNATURES = {
     "n2v_walk_consts": (C.c_int, [C.c_double, C.c_double, C.c_uint32, C.c_int, C.POINTER(WalkConsts)]),
     "n2v_ratio_build": (C.c_int, [C.POINTER(Graph), _P, _P]),
     "n2v_trim_sample": (C.c_int, [_P, _P, C.c_int64, C.c_int32, C.c_uint32, _P, _P, _P]),
+    "n2v_set_l2_fetch_granularity": (C.c_int, [C.c_int]),
+    "n2v_get_l2_fetch_granularity": (C.c_int, []),
     "n2v_first_occurrence_slots": (C.c_int64, [C.c_int64]),
     "n2v_first_occurrence": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_int64, _P, _P]),
     "n2v_vocab_count": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
@@ -124,6 +126,24 @@ def check(rc: int, what: str = ""):
 def current_stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_tuned = set()
+
+
+def tune_device(device_index=None):
+    """Once per device: L2 fetch granularity 32 bytes (the walk's gathers are single sectors; with the
+    default a miss drags in the whole 128-byte line).  N2V_L2_FETCH=0 leaves the driver's default,
+    N2V_L2_FETCH=64|128 sets another value (kernel-tuning runs)."""
+    import torch
+    idx = torch.cuda.current_device() if device_index is None else int(device_index)
+    if idx in _tuned:
+        return
+    _tuned.add(idx)
+    want = int(os.environ.get("N2V_L2_FETCH", "32"))
+    if want:
+        with torch.cuda.device(idx):
+            check(load().n2v_set_l2_fetch_granularity(want), "n2v_set_l2_fetch_granularity")
 
 
 def require_cuda():

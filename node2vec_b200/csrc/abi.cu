@@ -74,3 +74,15 @@ extern "C" int n2v_walk_consts(double return_param, double inout_param, uint32_t
   out->max_trials = 256;
   return N2V_OK;
 }
+
+extern "C" int n2v_set_l2_fetch_granularity(int bytes) {
+  N2V_CHECK_ARG(bytes == 32 || bytes == 64 || bytes == 128, "n2v_set_l2_fetch_granularity: %d is not 32, 64 or 128", bytes);
+  N2V_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(bytes)));
+  return N2V_OK;
+}
+
+extern "C" int n2v_get_l2_fetch_granularity(void) {
+  size_t v = 0;
+  if (cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity) != cudaSuccess) return -1;
+  return static_cast<int>(v);
+}

@@ -177,7 +177,7 @@ def trim_index(
     _reject_spark(compute_engine)
     df = _to_pandas(df_graph)
     if indexed is not True and torch.cuda.is_available() and set(df.columns) <= {"src", "dst", "weight"}:
-        res = _trim_index_frame_on_device(df, directed, max_out_deg, random_seed)
+        res = _index_graph_frame_on_device(df, directed, max_out_deg, random_seed)
         if res is not None:
             return res
     cap = max_out_deg if max_out_deg > 0 else MAX_OUT_DEGREES
@@ -201,29 +201,33 @@ def trim_index(
     return Frame(df_res.reset_index(drop=True)), Frame(name_id)
 
 
-def _trim_index_frame_on_device(df: pd.DataFrame, directed, max_out_deg, random_seed):
-    """trim_index for a pandas frame with the row-level work on the GPU (K5 trimming, K6 indexing and
-    de-duplication): one H2D of the columns, the reference's two frames back.  Integer names go to
-    the device as they are; other names (strings) are replaced on the host by their rank among the
-    sorted distinct names -- equality- and order-preserving, so partition order, first-occurrence
-    ids and the undirected expansion are unchanged -- and mapped back in the name table.
+def _frame_name_keys(df: pd.DataFrame):
+    """int64 keys for the ``src`` / ``dst`` names of a frame: integer names as they are, any other
+    names (strings) by their rank among the sorted distinct names (equality- and order-preserving).
+    Returns (src_key, dst_key, uniques or None, name dtype), or None when the names cannot be ranked."""
+    src, dst = df["src"].to_numpy(), df["dst"].to_numpy()
+    if src.dtype.kind in "iu" and dst.dtype.kind in "iu" and src.dtype != np.uint64 and dst.dtype != np.uint64:
+        return src.astype(np.int64), dst.astype(np.int64), None, (src.dtype if src.dtype == dst.dtype else object)
+    try:
+        codes, uniques = pd.factorize(np.concatenate([src.astype(object), dst.astype(object)]), sort=True)
+    except TypeError:
+        return None
+    if (codes < 0).any():
+        return None                                   # missing names: leave them to pandas' semantics
+    return codes[: len(src)].astype(np.int64), codes[len(src):].astype(np.int64), uniques, object
+
+
+def _index_graph_frame_on_device(df: pd.DataFrame, directed, max_out_deg=None, random_seed=None):
+    """``index_graph_pandas`` (and, with ``max_out_deg`` given, the partition + trim step before it)
+    for a pandas frame with the row-level work on the GPU (K5 trimming, K6 first-occurrence ids and
+    de-duplication): one H2D of the columns, the reference's two frames back.  Strings never go to the
+    device: they are replaced by ranks first and mapped back in the name table.
     Returns None when the names cannot be ranked (mixed types): the caller falls back to pandas."""
     from .preprocess import index_graph_device, trim_partitioned
-    src, dst = df["src"].to_numpy(), df["dst"].to_numpy()
-    uniques = None
-    if src.dtype.kind in "iu" and dst.dtype.kind in "iu" and src.dtype.itemsize <= 8 and dst.dtype.itemsize <= 8 \
-            and src.dtype != np.uint64 and dst.dtype != np.uint64:
-        s_key, d_key = src.astype(np.int64), dst.astype(np.int64)
-        name_dtype = src.dtype if src.dtype == dst.dtype else object
-    else:
-        try:
-            codes, uniques = pd.factorize(np.concatenate([src.astype(object), dst.astype(object)]), sort=True)
-        except TypeError:
-            return None
-        if (codes < 0).any():
-            return None                                   # missing names: leave them to pandas' semantics
-        s_key, d_key = codes[: len(src)].astype(np.int64), codes[len(src):].astype(np.int64)
-        name_dtype = object
+    keys = _frame_name_keys(df)
+    if keys is None:
+        return None
+    s_key, d_key, uniques, name_dtype = keys
     dev = torch.device("cuda", torch.cuda.current_device())
     ts, td = torch.as_tensor(s_key, device=dev), torch.as_tensor(d_key, device=dev)
     tw = None
@@ -231,7 +235,8 @@ def _trim_index_frame_on_device(df: pd.DataFrame, directed, max_out_deg, random_
         tw = torch.as_tensor(df["weight"].to_numpy().astype(np.float64), device=dev)
     else:
         df["weight"] = 1.0                                # the reference adds the column to the caller's frame too
-    ts, td, tw = trim_partitioned(ts, td, tw, max_out_deg, random_seed)
+    if max_out_deg is not None:
+        ts, td, tw = trim_partitioned(ts, td, tw, max_out_deg, random_seed)
     s, d, w, vid, vname = index_graph_device(ts, td, tw, directed)
     vname = vname.cpu().numpy()
     names = uniques[vname] if uniques is not None else (vname.astype(name_dtype) if name_dtype is not object
@@ -376,7 +381,7 @@ def random_walk(
             if n_vertices is None:
                 raise ValueError("a vertex-partitioned walk needs n_vertices (the global vertex count)")
             graph = own_graph = PartitionedGraph.from_local_arcs(src, dst, weight, int(n_vertices), group=process_group,
-                                                                 assume_symmetric=assume_symmetric)
+                                                                 assume_symmetric=assume_symmetric, keep_weight=False)
         else:
             graph = DeviceGraph.from_arcs(src, dst, weight, n_vertices=n_vertices)
     start = graph.start_vertices()

@@ -313,6 +313,10 @@ WALK_CASES = [
     (300, 2000, True, False, False, 4.0, 0.25, 2, 8),       # directed with sinks
     (50, 400, False, True, False, 100.0, 1000.0, 6, 5),      # fallback scans
     (2000, 40000, False, True, False, 0.5, 2.0, 2, 80),
+    (300, 3000, False, True, False, 0.25, 1.0, 4, 30),      # unit symmetric, q = 1: rho = 1/deg fold (mode 1)
+    (300, 3000, False, True, False, 0.2, 0.5, 4, 30),       # unit symmetric, p < q < 1: mode 1 with lookups
+    (300, 3000, False, True, False, 4.0, 2.0, 4, 30),       # mixture sampler, p > q > 1: x == prev thinned in the bulk
+    (400, 900, False, True, False, 1.0, 8.0, 6, 30),        # mixture sampler on a sparse graph (deg ~ 4): common-neighbour proposals mostly fail
 ]
 
 
@@ -340,8 +344,11 @@ def test_walk_equals_host_replay(n2v, case):
     # stats-free launch (the timed variant) gives the same walks
     walks2, alive2, _ = g.walk(start, nw, L, p, q, seed=4242, collect_stats=False)
     assert n2v.torch.equal(walks, walks2) and n2v.torch.equal(alive, alive2)
-    if case[5] == 0.25 and not weighted:
-        assert consts.fold_mode == 1 and stats["fold_hits"] > 0
+    assert np.float32(consts.mix_qm1) == np.float32(oc.mix_qm1)
+    if not weighted and sym and not multi:
+        assert consts.fold_mode == (3 if q > 1.0 else 1 if p < min(1.0, q) else 0)
+    if case[5] in (0.25, 0.2) and not weighted:
+        assert stats["fold_hits"] > 0
     if need_ratio:
         assert consts.fold_mode == 2 and g.ratio is not None and stats["fold_hits"] > 0
     if p == 100.0:
@@ -495,7 +502,7 @@ def test_plain_c_consumer():
     exe = nb.build_c_consumer()
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr + out.stdout
-    assert out.stdout.startswith("c_consumer OK abi=6") and "dropped_at_sink=" in out.stdout
+    assert out.stdout.startswith("c_consumer OK abi=7") and "dropped_at_sink=" in out.stdout
     fields = dict(kv.split("=") for kv in out.stdout.split()[2:])
     assert int(fields["walkers"]) == 999 * 4 and int(fields["alive"]) + int(fields["dropped_at_sink"]) == 999 * 4
     assert int(fields["dropped_at_sink"]) > 0 and int(fields["alive"]) > 0
