@@ -260,11 +260,11 @@ int n2v_walk_consts(double return_param, double inout_param, uint32_t graph_flag
 int n2v_ratio_build(const n2v_graph_t* graph, float* ratio_out, void* stream);
 
 /* ---- device tuning: L2 fetch granularity ------------------------------------------------
- * The walk is a stream of random 32-byte gathers (one arc record / one hash bucket each).  With the
- * driver's default L2 fetch granularity a missing sector pulls its whole 128-byte line from HBM:
- * ncu on the RMAT-20 walk shows 3.4 DRAM sectors per requested sector (profiles/).  Setting
- * cudaLimitMaxL2FetchGranularity to 32 makes L2 fetch what was asked for.  The limit is a property
- * of the CUDA context (all kernels of the process on this device), a performance hint only.
+ * The walk is a stream of random 32-byte gathers (one arc record / one hash bucket each); ncu on
+ * the RMAT-20 walk shows 3.4 DRAM sectors read per requested sector (profiles/r02_walk_ncu.txt).
+ * cudaLimitMaxL2FetchGranularity (a context-wide performance hint) is exposed for tuning runs;
+ * measured on B200 it changes nothing (42.6 G random sectors/s at 32, 64 = default and 128,
+ * profiles/r02_gather_granule_l2fetch.txt), so nothing in the package sets it by default.
  * bytes: 32, 64 or 128.  get returns the current limit (or -1 on error). */
 int n2v_set_l2_fetch_granularity(int bytes);
 int n2v_get_l2_fetch_granularity(void);

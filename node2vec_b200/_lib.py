@@ -132,15 +132,16 @@ _tuned = set()
 
 
 def tune_device(device_index=None):
-    """Once per device: L2 fetch granularity 32 bytes (the walk's gathers are single sectors; with the
-    default a miss drags in the whole 128-byte line).  N2V_L2_FETCH=0 leaves the driver's default,
-    N2V_L2_FETCH=64|128 sets another value (kernel-tuning runs)."""
+    """Optional per-device tuning knob: N2V_L2_FETCH=32|64|128 sets cudaLimitMaxL2FetchGranularity
+    before the first walk.  Measured on B200 (profiles/r02_gather_granule_l2fetch.txt): the random
+    32-byte gather rate is 42.6 G sectors/s at 32, 64 (driver default) and 128 alike, so the default
+    is to leave the driver's value alone."""
     import torch
     idx = torch.cuda.current_device() if device_index is None else int(device_index)
     if idx in _tuned:
         return
     _tuned.add(idx)
-    want = int(os.environ.get("N2V_L2_FETCH", "32"))
+    want = int(os.environ.get("N2V_L2_FETCH", "0"))
     if want:
         with torch.cuda.device(idx):
             check(load().n2v_set_l2_fetch_granularity(want), "n2v_set_l2_fetch_granularity")

@@ -20,6 +20,8 @@
 // tens of thousands of concurrent warps) or plain stores (gensim's own lock-free behaviour).
 // This is a gather/scatter path -- (K+2) rows in, (K+2) rows out per pair -- so no tensor
 // cores; the walk buffer is read once per epoch.
+#include <stdlib.h>
+
 #include "n2v_internal.cuh"
 
 namespace {
@@ -160,7 +162,25 @@ __device__ __forceinline__ float gradient(const float* table, float f, float lab
   return ok ? g : 0.0f;
 }
 
-template <int NV, bool ATOMIC, bool TRACE, bool FULL>
+// one negative ~ count^0.75 from the (two-level) alias table; consumes 2 (4) draws of the walk's stream
+__device__ __forceinline__ int32_t draw_negative(const SgnsArgs& A, uint32_t& rnd) {
+  uint32_t lo = 0, span = A.n_vertices;
+  if (A.n_top) {   // two-level table: chunk ~ mass first (top level is L2-resident)
+    const uint32_t c0 = __umulhi(pcg_next(rnd), A.n_top);
+    const int2 te = __ldg(A.neg_table + A.n_vertices + c0);
+    const uint32_t c = (pcg_next(rnd) < static_cast<uint32_t>(te.x)) ? c0 : static_cast<uint32_t>(te.y);
+    lo = c * N2V_NEG_CHUNK;
+    span = min(static_cast<uint32_t>(N2V_NEG_CHUNK), A.n_vertices - lo);
+  }
+  const uint32_t u1 = pcg_next(rnd);
+  const uint32_t u2 = pcg_next(rnd);
+  const uint32_t slot = lo + __umulhi(u1, span);
+  const int2 e = __ldg(A.neg_table + slot);
+  return (u2 < static_cast<uint32_t>(e.x)) ? static_cast<int32_t>(slot) : e.y;
+}
+
+// PREFETCH: draw the pair's K negatives first and prefetch their rows into L2 (tables beyond L2)
+template <int NV, bool ATOMIC, bool TRACE, bool FULL, bool PREFETCH>
 __global__ void __launch_bounds__(kBlock, NV == 1 ? N2V_SGNS_MIN_BLOCKS : (NV == 2 ? N2V_SGNS_MIN_BLOCKS_NV2 : 1))
 sgns_kernel(const __grid_constant__ SgnsArgs A) {
   extern __shared__ int32_t smem[];
@@ -240,6 +260,32 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
         if (j == i) continue;
         const int32_t wj = sent[j];
         float* in_ptr = A.syn0 + static_cast<int64_t>(wj) * A.dim;
+        // K negatives ~ count^0.75, one 8-byte alias gather each.  The K targets of the pair are drawn up
+        // front (same draws in the same order as drawing them one by one: nothing else consumes the
+        // walk's stream in between), lane d keeps target d, and their rows are prefetched into L2 with
+        // ONE warp-wide prefetch (a lane per 128-byte line) while the input row is loaded and the positive target is processed -- the
+        // sequential target loop below then pays L2 instead of HBM latency for tables beyond L2.
+        int32_t my_tgt = 0;
+        if (PREFETCH) {
+          for (int d = 0; d < K; ++d) {
+            const int32_t tgt = draw_negative(A, rnd);
+            if (lane == d) my_tgt = tgt;
+          }
+          const int lines = (A.dim * 4 + 127) >> 7;          // 128-byte lines per row
+          for (int first = 0; first < K * lines; first += 32) {
+            const int idx = first + lane;
+            const int d = min(idx / lines, K - 1);
+            const int32_t t = __shfl_sync(0xffffffffu, my_tgt, d);
+            if (idx < K * lines) {
+              const float* line = A.syn1neg + static_cast<int64_t>(t) * A.dim + (idx - d * lines) * 32;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+            }
+          }
+          if (j + 1 < j1 && lane < lines) {                  // next context row of this centre (skips i itself)
+            const int jn = (j + 1 == i) ? j + 2 : j + 1;
+            if (jn < j1) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.syn0 + static_cast<int64_t>(sent[jn]) * A.dim + lane * 32));
+          }
+        }
         const Row<NV> in = load_row<NV, FULL>(in_ptr, A.dim, lane);
         Row<NV> work;
 #pragma unroll
@@ -260,21 +306,9 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
           axpy<NV>(pos, g, in);
           if (ATOMIC) axpy<NV>(pos_delta, g, in);
         }
-        // K negatives ~ count^0.75, one 8-byte alias gather each
+        // K negatives ~ count^0.75 (drawn at the top of the pair when PREFETCH, else one by one here)
         for (int d = 0; d < K; ++d) {
-          uint32_t lo = 0, span = A.n_vertices;
-          if (A.n_top) {   // two-level table: chunk ~ mass first (top level is L2-resident)
-            const uint32_t c0 = __umulhi(pcg_next(rnd), A.n_top);
-            const int2 te = __ldg(A.neg_table + A.n_vertices + c0);
-            const uint32_t c = (pcg_next(rnd) < static_cast<uint32_t>(te.x)) ? c0 : static_cast<uint32_t>(te.y);
-            lo = c * N2V_NEG_CHUNK;
-            span = min(static_cast<uint32_t>(N2V_NEG_CHUNK), A.n_vertices - lo);
-          }
-          const uint32_t u1 = pcg_next(rnd);
-          const uint32_t u2 = pcg_next(rnd);
-          const uint32_t slot = lo + __umulhi(u1, span);
-          const int2 e = __ldg(A.neg_table + slot);
-          const int32_t tgt = (u2 < static_cast<uint32_t>(e.x)) ? static_cast<int32_t>(slot) : e.y;
+          const int32_t tgt = PREFETCH ? __shfl_sync(0xffffffffu, my_tgt, d) : draw_negative(A, rnd);
           const bool skip = tgt == wi;                      // gensim: a negative equal to the centre is skipped
           if (TRACE && trow && lane == 0) trow[2 + d] = skip ? -1 : tgt;
           float* t_ptr = A.syn1neg + static_cast<int64_t>(tgt) * A.dim;
@@ -315,14 +349,14 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
   }
 }
 
-template <int NV, bool FULL>
+template <int NV, bool FULL, bool PREFETCH>
 cudaError_t launch_full(const SgnsArgs& A, bool atomic, int grid, size_t smem, cudaStream_t stream) {
-#define N2V_SGNS_GO(AT, TR)                                                                              \
-  do {                                                                                                   \
-    if (smem > 48 * 1024)                                                                                \
-      cudaFuncSetAttribute(sgns_kernel<NV, AT, TR, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                           static_cast<int>(smem));                                                      \
-    sgns_kernel<NV, AT, TR, FULL><<<grid, kBlock, smem, stream>>>(A);                                   \
+#define N2V_SGNS_GO(AT, TR)                                                                                        \
+  do {                                                                                                             \
+    if (smem > 48 * 1024)                                                                                          \
+      cudaFuncSetAttribute(sgns_kernel<NV, AT, TR, FULL, PREFETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                           static_cast<int>(smem));                                                                \
+    sgns_kernel<NV, AT, TR, FULL, PREFETCH><<<grid, kBlock, smem, stream>>>(A);                                   \
   } while (0)
   if (A.trace) {
     if (atomic) N2V_SGNS_GO(true, true); else N2V_SGNS_GO(false, true);
@@ -334,9 +368,12 @@ cudaError_t launch_full(const SgnsArgs& A, bool atomic, int grid, size_t smem, c
 }
 
 template <int NV>
-cudaError_t launch(const SgnsArgs& A, bool atomic, int grid, size_t smem, cudaStream_t stream) {
-  return A.dim == NV * 128 ? launch_full<NV, true>(A, atomic, grid, smem, stream)
-                           : launch_full<NV, false>(A, atomic, grid, smem, stream);
+cudaError_t launch(const SgnsArgs& A, bool atomic, bool prefetch, int grid, size_t smem, cudaStream_t stream) {
+  if (A.dim == NV * 128)
+    return prefetch ? launch_full<NV, true, true>(A, atomic, grid, smem, stream)
+                    : launch_full<NV, true, false>(A, atomic, grid, smem, stream);
+  return prefetch ? launch_full<NV, false, true>(A, atomic, grid, smem, stream)
+                  : launch_full<NV, false, false>(A, atomic, grid, smem, stream);
 }
 
 }  // namespace
@@ -405,7 +442,12 @@ extern "C" int n2v_sgns_train(const int32_t* walks, int64_t n_walks, int32_t len
   const int nv = (P->dim + 127) / 128;
   cudaError_t err;
   const bool atomic = P->atomic_updates != 0;
-#define N2V_SGNS_LAUNCH(NVV) err = launch<NVV>(A, atomic, grid, smem, stream)
+  // negative-row prefetch: on when both tables together exceed what L2 can hold (rows then come from HBM
+  // and the dependent target loop is latency-bound); N2V_SGNS_PREFETCH=0|1 overrides (tests, tuning)
+  bool prefetch = 2.0 * static_cast<double>(n_vertices) * P->dim * 4.0 > 96.0e6;
+  if (const char* e = getenv("N2V_SGNS_PREFETCH")) prefetch = e[0] == '1';
+  prefetch = prefetch && P->negative <= 32;
+#define N2V_SGNS_LAUNCH(NVV) err = launch<NVV>(A, atomic, prefetch, grid, smem, stream)
   if (nv <= 1) N2V_SGNS_LAUNCH(1);
   else if (nv <= 2) N2V_SGNS_LAUNCH(2);
   else if (nv <= 4) N2V_SGNS_LAUNCH(4);
