@@ -734,8 +734,12 @@ def multi_gpu_parity(torch, dist, dev, rank, world):
 
 def tables_identical(torch, dist, m, dev, world):
     """After an averaging step every rank must hold bit-identical tables."""
-    sig = torch.stack([m.syn0.view(torch.int32).sum(dtype=torch.int64), m.syn1neg.view(torch.int32).sum(dtype=torch.int64),
-                       m.syn0.view(torch.int32)[:: 4097].sum(dtype=torch.int64)])
+    def checksum(t):                       # int64 sum of the fp32 bit patterns, in row blocks (no table-sized temporary)
+        bits, tot = t.view(torch.int32), torch.zeros((), dtype=torch.int64, device=dev)
+        for lo in range(0, bits.shape[0], 1 << 20):
+            tot += bits[lo:lo + (1 << 20)].sum(dtype=torch.int64)
+        return tot
+    sig = torch.stack([checksum(m.syn0), checksum(m.syn1neg), m.syn0.view(torch.int32)[:: 4097].sum(dtype=torch.int64)])
     allsig = [torch.empty_like(sig) for _ in range(world)]
     dist.all_gather(allsig, sig)
     return all(bool(torch.equal(allsig[0], s)) for s in allsig)

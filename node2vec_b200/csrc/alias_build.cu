@@ -325,7 +325,7 @@ __global__ void alias_draw_kernel(const int32_t* __restrict__ alias, const doubl
 
 inline int grid_for(int64_t n) {
   const int64_t need = (n + kBlock - 1) / kBlock;
-  const int64_t cap = int64_t(n2v::kSmCount) * 16;
+  const int64_t cap = int64_t(n2v::sm_count()) * 16;
   return static_cast<int>(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
@@ -357,7 +357,7 @@ extern "C" int n2v_alias_build(n2v_vertex_t* vtx, const n2v_vertex_t* vtx_lookup
                                                                    d_hubs, d_nhubs, d_giants, d_ngiants);
   N2V_LAUNCH_OK();
   if (n_arcs > kHubMax) {
-    const int64_t grid = max_giants < 4 * n2v::kSmCount ? max_giants : 4 * n2v::kSmCount;
+    const int64_t grid = max_giants < 4 * n2v::sm_count() ? max_giants : 4 * n2v::sm_count();
     alias_giant_kernel<<<static_cast<unsigned int>(grid), kHubBlock, 0, stream>>>(
         vtx, lookup, col, weight_sorted, sum_mode, alias, probs, arcs, scratch, d_giants, d_ngiants, d_zero);
     N2V_LAUNCH_OK();
@@ -367,7 +367,7 @@ extern "C" int n2v_alias_build(n2v_vertex_t* vtx, const n2v_vertex_t* vtx_lookup
     // exits at once when it is empty
     const size_t smem = static_cast<size_t>(kHubMax) * 16;
     N2V_CUDA(cudaFuncSetAttribute(alias_hub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    const int64_t grid = max_hubs < n2v::kSmCount ? max_hubs : n2v::kSmCount;
+    const int64_t grid = max_hubs < n2v::sm_count() ? max_hubs : n2v::sm_count();
     alias_hub_kernel<<<static_cast<unsigned int>(grid), kHubBlock, smem, stream>>>(
         vtx, lookup, col, weight_sorted, sum_mode, alias, probs, arcs, d_hubs, d_nhubs, d_zero);
     N2V_LAUNCH_OK();

@@ -13,7 +13,7 @@ inline int64_t align256(int64_t x) { return (x + 255) & ~int64_t(255); }
 
 inline int grid_for(int64_t n, int per_sm = 8) {
   const int64_t need = (n + kBlock - 1) / kBlock;
-  const int64_t cap = int64_t(n2v::kSmCount) * per_sm;
+  const int64_t cap = int64_t(n2v::sm_count()) * per_sm;
   return static_cast<int>(need < cap ? (need > 0 ? need : 1) : cap);
 }
 

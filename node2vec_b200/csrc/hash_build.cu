@@ -10,7 +10,7 @@ constexpr int kBlock = 128;
 
 inline int grid_for(int64_t n_warps_needed) {
   const int64_t need = (n_warps_needed * 32 + kBlock - 1) / kBlock;
-  const int64_t cap = int64_t(n2v::kSmCount) * 16;
+  const int64_t cap = int64_t(n2v::sm_count()) * 16;
   return static_cast<int>(need < cap ? (need > 0 ? need : 1) : cap);
 }
 

@@ -52,7 +52,7 @@ __device__ __forceinline__ bool same_key(const Keys& K, int64_t a, int64_t b) {
 
 inline int grid_for(int64_t n) {
   const int64_t need = (n + kBlock - 1) / kBlock;
-  const int64_t cap = int64_t(n2v::kSmCount) * 16;
+  const int64_t cap = int64_t(n2v::sm_count()) * 16;
   return static_cast<int>(need < cap ? (need > 0 ? need : 1) : cap);
 }
 

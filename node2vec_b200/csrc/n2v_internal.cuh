@@ -30,7 +30,19 @@ void set_error(const char* fmt, ...);
 // launch-error check that does not synchronise
 #define N2V_LAUNCH_OK() N2V_CUDA(cudaGetLastError())
 
-constexpr int kSmCount = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+// SMs of the current device (B200: 148 = 2 dies x 74); grids are sized in multiples of this.
+// Queried once per host thread and device; 148 if the query fails.
+inline int sm_count() {
+  static thread_local int cached_dev = -1, cached = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    cached = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    cached_dev = dev;
+  }
+  return cached;
+}
 
 // ---- 16-byte record loads (one LDG.128 each, read-only path) ------------------------
 // {base, deg, hbase, wsum-bits} of a vertex in one load

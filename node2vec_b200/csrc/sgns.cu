@@ -436,15 +436,16 @@ extern "C" int n2v_sgns_train(const int32_t* walks, int64_t n_walks, int32_t len
   if (trace) grid = 1;  // the kernel lets only warp 0 work in trace mode
   else {
     const int64_t need = (n_walks + kWarps - 1) / kWarps;
-    const int64_t cap = int64_t(n2v::kSmCount) * 8;
+    const int64_t cap = int64_t(n2v::sm_count()) * 8;
     grid = static_cast<int>(need < cap ? need : cap);
   }
   const int nv = (P->dim + 127) / 128;
   cudaError_t err;
   const bool atomic = P->atomic_updates != 0;
-  // negative-row prefetch: on when both tables together exceed what L2 can hold (rows then come from HBM
-  // and the dependent target loop is latency-bound); N2V_SGNS_PREFETCH=0|1 overrides (tests, tuning)
-  bool prefetch = 2.0 * static_cast<double>(n_vertices) * P->dim * 4.0 > 96.0e6;
+  // negative-row prefetch variant: OFF by default.  Measured on configs[2] (tables 2 x 0.54 GB, 70 % L2 hits):
+  // 5199 vs 5120 ms per epoch -- the kernel is bound by the row gather + reduction rate, not by the latency
+  // of the dependent target loop (profiles/README.md).  N2V_SGNS_PREFETCH=1 selects it (tests, tuning).
+  bool prefetch = false;
   if (const char* e = getenv("N2V_SGNS_PREFETCH")) prefetch = e[0] == '1';
   prefetch = prefetch && P->negative <= 32;
 #define N2V_SGNS_LAUNCH(NVV) err = launch<NVV>(A, atomic, prefetch, grid, smem, stream)

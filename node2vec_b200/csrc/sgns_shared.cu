@@ -296,7 +296,7 @@ extern "C" int n2v_sgns_train_shared(const int32_t* walks, int64_t n_walks, int3
   if (trace) grid = 1;
   else {
     const int64_t need = (n_walks + kWarps - 1) / kWarps;
-    const int64_t cap = int64_t(n2v::kSmCount) * 8;
+    const int64_t cap = int64_t(n2v::sm_count()) * 8;
     grid = static_cast<int>(need < cap ? need : cap);
   }
   const bool full = P->dim == 128;

@@ -12,7 +12,7 @@ constexpr int kBlock = 256;
 
 inline int grid_for(int64_t n) {
   const int64_t need = (n + kBlock - 1) / kBlock;
-  const int64_t cap = int64_t(n2v::kSmCount) * 8;
+  const int64_t cap = int64_t(n2v::sm_count()) * 8;
   return static_cast<int>(need < cap ? (need > 0 ? need : 1) : cap);
 }
 

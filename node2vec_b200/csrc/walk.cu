@@ -408,7 +408,7 @@ extern "C" int n2v_walk(const n2v_graph_t* graph, const int32_t* start, int64_t 
     A.walks = walks + w0 * pitch;
     A.alive = alive + w0;
     const int64_t need = (n + kBlock - 1) / kBlock;
-    const int64_t cap = int64_t(n2v::kSmCount) * kBlocksPerSm;
+    const int64_t cap = int64_t(n2v::sm_count()) * kBlocksPerSm;
     const int grid = static_cast<int>(need < cap ? need : cap);
 #define N2V_LAUNCH_WALK(F, M, S) walk_kernel<F, M, S><<<grid, kBlock, 0, stream>>>(*graph, A)
     switch (fold * 4 + (multi ? 2 : 0) + (st ? 1 : 0)) {

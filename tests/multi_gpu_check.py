@@ -66,6 +66,20 @@ def main():
         dist.barrier()
         part.close()
         del full
+    # the public entry point in partitioned mode: fugue.random_walk(process_group=...) on this rank's arcs returns
+    # the rows a single GPU holding the whole graph returns for this rank's start vertices
+    from node2vec_b200 import fugue
+    S = (V + world - 1) // world
+    mine = (src >= rank * S) & (src < (rank + 1) * S)
+    prm = {"num_walks": 3, "walk_length": 12, "return_param": 0.25, "inout_param": 4.0}
+    host = torch.empty((S * 3, 13), dtype=torch.int32, pin_memory=True)
+    res = fugue.random_walk(None, (src[mine], dst[mine]), dict(prm), None, random_seed=21, process_group=dist.group.WORLD,
+                            n_vertices=V, assume_symmetric=True, out=host)
+    whole = fugue.random_walk(None, (src, dst), dict(prm), None, random_seed=21, n_vertices=V)
+    lo, hi = rank * S, (rank + 1) * S
+    want = whole.walks[(whole.walks[:, 0] >= lo) & (whole.walks[:, 0] < hi)]
+    assert np.array_equal(res.walks, want) and np.array_equal(host.numpy()[: len(want)], want), "random_walk(process_group)"
+    dist.barrier()
     # data-parallel SGNS: every rank trains on its own walks, tables averaged every epoch
     g = DeviceGraph.from_arcs(src, dst, None, n_vertices=V)
     start = n2v_dist.shard_start_vertices(g.start_vertices(), rank, world)
