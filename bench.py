@@ -171,8 +171,11 @@ def walk_roofline(stats, steps_per_launch, kernel_ms, level, workload, note, rem
         c = 1.0 / (remote_frac / ceil["nvlink_peer"] + (1.0 - remote_frac) / ceil["hbm"])
     else:
         c = ceil[level]
+    traffic = ncu_traffic(workload, "walk_kernel")
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": ncu_traffic(workload, "walk_kernel"), "kernel": "walk_kernel", "bytes_per_step": b_step,
+            "traffic": traffic, "kernel": "walk_kernel", "bytes_per_step": b_step,
+            # ncu DRAM bytes of one launch of this workload over THIS run's kernel time, as a fraction of the copy peak
+            "traffic_frac_of_peak": (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if traffic else None,
             "bytes_per_step_formula": "16 + T*(12 + 4*l) + 4 (SURVEY 8d)",
             "algorithmic_bytes_per_launch": steps_per_launch * b_step, "steps_per_launch": steps_per_launch,
             "trials_per_step": T, "probes_per_trial": lp, "sectors_per_step": sectors,
@@ -551,6 +554,8 @@ def sgns_block(torch, walks, host_walks, w, name, flush, steps, warmup, e2e_pass
                         "median of %d passes" % e2e_passes},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(name, "sgns_kernel"), "kernel": "sgns_kernel",
+                     "traffic_frac_of_peak": (ncu_traffic(name, "sgns_kernel") / (kernel_ms * 1e-3) / 1e9 / peak)
+                     if ncu_traffic(name, "sgns_kernel") else None,
                      "bytes_per_pair": b_pair, "kernel_ms": kernel_ms,
                      "algorithmic_bytes_per_launch": per_launch * b_pair, "pairs_per_launch": per_launch,
                      "peak_source": peak_src, "note": table_note},
@@ -849,6 +854,14 @@ def bench_partitioned(args):
     log(f"[rank {rank}] walk {kernel_ms:.1f} ms/pass, {steps_per_pass / kernel_ms / 1e6:.2f} G steps/s on this rank, "
         f"{remote:.0%} remote hops")
 
+    # the graph is not needed any more: unmap the peers' parts and free this rank's (collective) before the
+    # 2 x 34 GB tables are allocated
+    n_arcs_total = int(g.n_arcs)
+    sync_all()
+    g.close()
+    del g
+    torch.cuda.empty_cache()
+
     # ---- SGNS: data-parallel over the rank's own walks, replicated tables averaged by NCCL
     sgns = None
     parity_tables = None
@@ -953,14 +966,13 @@ def bench_partitioned(args):
             "vocab_s": t_vocab,
         }
     sync_all()
-    g.close()
     if rank == 0:
         line = {
             "metric": "walk_steps_per_s", "value": value, "unit": "walk-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": workload_config(name, w, world),
-            "detail": {"vertices": V, "arcs": int(g.n_arcs),
+            "detail": {"vertices": V, "arcs": n_arcs_total,
                        "arcs_per_gpu": n_local_arcs, "graph_bytes_per_gpu": graph_bytes, "walkers_per_gpu": W,
                        "sharding": "vertex-partitioned CSR (rank r owns vertices [r*S, (r+1)*S) and their arc records / "
                                    "hash sets), peers read over NVLink with plain LDG.256; walkers stay on the rank of "

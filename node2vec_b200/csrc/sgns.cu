@@ -35,6 +35,7 @@ constexpr int kWarps = kBlock / 32;
 #define N2V_SGNS_MIN_BLOCKS_NV2 3
 #endif
 constexpr float kMaxExp = 6.0f;
+constexpr int kDefaultMode = 0;   // see sgns_kernel MODE; chosen by measurement (profiles/README.md)
 
 struct SgnsArgs {
   const int32_t* walks;
@@ -179,8 +180,15 @@ __device__ __forceinline__ int32_t draw_negative(const SgnsArgs& A, uint32_t& rn
   return (u2 < static_cast<uint32_t>(e.x)) ? static_cast<int32_t>(slot) : e.y;
 }
 
-// PREFETCH: draw the pair's K negatives first and prefetch their rows into L2 (tables beyond L2)
-template <int NV, bool ATOMIC, bool TRACE, bool FULL, bool PREFETCH>
+// MODE (latency hiding for tables beyond L2; every mode makes the same draws and the same arithmetic):
+//   0  one negative at a time: draw -> alias entry -> row -> update (2 dependent round trips per negative)
+//   1  the pair's K negatives drawn first (sequentially), their rows prefetched into L2 by one warp-wide
+//      prefetch, then processed one by one
+//   2  as 1, but lane d draws negative d from the walk's PCG stream jumped ahead to draw d's position (the
+//      LCG state after n steps is s * a^n + c * (a^n - 1) / (a - 1)): the K alias-entry gathers become ONE
+//      warp-wide gather instead of K dependent ones
+//   3  as 2, and the next target row is loaded while the current one is processed (double buffering)
+template <int NV, bool ATOMIC, bool TRACE, bool FULL, int MODE>
 __global__ void __launch_bounds__(kBlock, NV == 1 ? N2V_SGNS_MIN_BLOCKS : (NV == 2 ? N2V_SGNS_MIN_BLOCKS_NV2 : 1))
 sgns_kernel(const __grid_constant__ SgnsArgs A) {
   extern __shared__ int32_t smem[];
@@ -197,6 +205,17 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
   uint32_t c_negskip = 0, c_clip = 0;   // per-warp; far below 2^32 per launch share
   int64_t trace_pos = 0;
   const int K = A.negative;
+  // PCG jump-ahead constants: (jA, jC) takes the stream from a pair's first negative draw to lane d's
+  // negative (d * draws_per_negative steps), (kA, kC) past all K negatives
+  uint32_t jA = 1u, jC = 0u, kA = 1u, kC = 0u;
+  if (MODE >= 2) {
+    const int per = A.n_top ? 4 : 2;
+    for (int n = 0; n < K * per; ++n) {
+      if (n == lane * per) { jA = kA; jC = kC; }
+      kA *= 747796405u;
+      kC = kC * 747796405u + 2891336453u;
+    }
+  }
   const double total_words = static_cast<double>(A.total_walks) * static_cast<double>(A.len);
 
   for (int64_t s = tracing ? 0 : static_cast<int64_t>(blockIdx.x) * kWarps + wib; s < A.n_walks; s += n_warps) {
@@ -260,16 +279,22 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
         if (j == i) continue;
         const int32_t wj = sent[j];
         float* in_ptr = A.syn0 + static_cast<int64_t>(wj) * A.dim;
-        // K negatives ~ count^0.75, one 8-byte alias gather each.  The K targets of the pair are drawn up
-        // front (same draws in the same order as drawing them one by one: nothing else consumes the
-        // walk's stream in between), lane d keeps target d, and their rows are prefetched into L2 with
-        // ONE warp-wide prefetch (a lane per 128-byte line) while the input row is loaded and the positive target is processed -- the
-        // sequential target loop below then pays L2 instead of HBM latency for tables beyond L2.
+        // K negatives ~ count^0.75, one 8-byte alias gather each.  MODE >= 1: the K targets of the pair are
+        // drawn up front (the same draws in the same order as drawing them one by one: nothing else consumes
+        // the walk's stream in between), lane d keeps target d, and their rows are prefetched into L2
+        // with ONE warp-wide prefetch (a lane per 128-byte line) while the input row is loaded and the
+        // positive target is processed.
         int32_t my_tgt = 0;
-        if (PREFETCH) {
-          for (int d = 0; d < K; ++d) {
-            const int32_t tgt = draw_negative(A, rnd);
-            if (lane == d) my_tgt = tgt;
+        if (MODE >= 1) {
+          if (MODE == 1) {
+            for (int d = 0; d < K; ++d) {
+              const int32_t tgt = draw_negative(A, rnd);
+              if (lane == d) my_tgt = tgt;
+            }
+          } else {
+            uint32_t mine = rnd * jA + jC;                    // the stream at lane d's negative
+            if (lane < K) my_tgt = draw_negative(A, mine);    // K alias gathers in one warp-wide load
+            rnd = rnd * kA + kC;                              // past all K negatives
           }
           const int lines = (A.dim * 4 + 127) >> 7;          // 128-byte lines per row
           for (int first = 0; first < K * lines; first += 32) {
@@ -306,13 +331,30 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
           axpy<NV>(pos, g, in);
           if (ATOMIC) axpy<NV>(pos_delta, g, in);
         }
-        // K negatives ~ count^0.75 (drawn at the top of the pair when PREFETCH, else one by one here)
+        // the K negative targets, in order (drawn at the top of the pair when MODE >= 1, else one by one here)
+        Row<NV> ahead;                                        // MODE 3: row of the NEXT target, loaded early
+        int32_t tgt_ahead = 0;
+        if (MODE == 3) {
+          tgt_ahead = __shfl_sync(0xffffffffu, my_tgt, 0);
+          ahead = load_row<NV, FULL>(A.syn1neg + static_cast<int64_t>(tgt_ahead) * A.dim, A.dim, lane);
+        }
         for (int d = 0; d < K; ++d) {
-          const int32_t tgt = PREFETCH ? __shfl_sync(0xffffffffu, my_tgt, d) : draw_negative(A, rnd);
+          const int32_t tgt = MODE == 3 ? tgt_ahead : MODE >= 1 ? __shfl_sync(0xffffffffu, my_tgt, d) : draw_negative(A, rnd);
           const bool skip = tgt == wi;                      // gensim: a negative equal to the centre is skipped
           if (TRACE && trow && lane == 0) trow[2 + d] = skip ? -1 : tgt;
           float* t_ptr = A.syn1neg + static_cast<int64_t>(tgt) * A.dim;
-          const Row<NV> tr = load_row<NV, FULL>(t_ptr, A.dim, lane);
+          Row<NV> tr;
+          if (MODE == 3) {
+            tr = ahead;
+            if (d + 1 < K) {
+              tgt_ahead = __shfl_sync(0xffffffffu, my_tgt, d + 1);
+              // a repeated target must see this target's update: it is (re)loaded after the update below
+              if (tgt_ahead != tgt)
+                ahead = load_row<NV, FULL>(A.syn1neg + static_cast<int64_t>(tgt_ahead) * A.dim, A.dim, lane);
+            }
+          } else {
+            tr = load_row<NV, FULL>(t_ptr, A.dim, lane);
+          }
           const float f = dot_rows<NV>(in, tr);
           const bool in_range = f > -kMaxExp && f < kMaxExp;
           const bool ok = in_range && !skip;
@@ -323,6 +365,8 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
           }
           axpy<NV>(work, g, tr);
           if (ATOMIC || ok) update_row<NV, ATOMIC, FULL>(t_ptr, A.dim, lane, g, in, tr);
+          if (MODE == 3 && d + 1 < K && tgt_ahead == tgt)
+            ahead = load_row<NV, FULL>(t_ptr, A.dim, lane);
         }
         add_row<NV, ATOMIC, FULL>(in_ptr, A.dim, lane, work, in);
         ++c_pairs;
@@ -349,14 +393,14 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
   }
 }
 
-template <int NV, bool FULL, bool PREFETCH>
+template <int NV, bool FULL, int MODE>
 cudaError_t launch_full(const SgnsArgs& A, bool atomic, int grid, size_t smem, cudaStream_t stream) {
 #define N2V_SGNS_GO(AT, TR)                                                                                        \
   do {                                                                                                             \
     if (smem > 48 * 1024)                                                                                          \
-      cudaFuncSetAttribute(sgns_kernel<NV, AT, TR, FULL, PREFETCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+      cudaFuncSetAttribute(sgns_kernel<NV, AT, TR, FULL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                            static_cast<int>(smem));                                                                \
-    sgns_kernel<NV, AT, TR, FULL, PREFETCH><<<grid, kBlock, smem, stream>>>(A);                                   \
+    sgns_kernel<NV, AT, TR, FULL, MODE><<<grid, kBlock, smem, stream>>>(A);                                   \
   } while (0)
   if (A.trace) {
     if (atomic) N2V_SGNS_GO(true, true); else N2V_SGNS_GO(false, true);
@@ -367,13 +411,20 @@ cudaError_t launch_full(const SgnsArgs& A, bool atomic, int grid, size_t smem, c
   return cudaGetLastError();
 }
 
+template <int NV, bool FULL>
+cudaError_t launch_mode(const SgnsArgs& A, bool atomic, int mode, int grid, size_t smem, cudaStream_t stream) {
+  switch (mode) {
+    case 1: return launch_full<NV, FULL, 1>(A, atomic, grid, smem, stream);
+    case 2: return launch_full<NV, FULL, 2>(A, atomic, grid, smem, stream);
+    case 3: return launch_full<NV, FULL, 3>(A, atomic, grid, smem, stream);
+    default: return launch_full<NV, FULL, 0>(A, atomic, grid, smem, stream);
+  }
+}
+
 template <int NV>
-cudaError_t launch(const SgnsArgs& A, bool atomic, bool prefetch, int grid, size_t smem, cudaStream_t stream) {
-  if (A.dim == NV * 128)
-    return prefetch ? launch_full<NV, true, true>(A, atomic, grid, smem, stream)
-                    : launch_full<NV, true, false>(A, atomic, grid, smem, stream);
-  return prefetch ? launch_full<NV, false, true>(A, atomic, grid, smem, stream)
-                  : launch_full<NV, false, false>(A, atomic, grid, smem, stream);
+cudaError_t launch(const SgnsArgs& A, bool atomic, int mode, int grid, size_t smem, cudaStream_t stream) {
+  return A.dim == NV * 128 ? launch_mode<NV, true>(A, atomic, mode, grid, smem, stream)
+                           : launch_mode<NV, false>(A, atomic, mode, grid, smem, stream);
 }
 
 }  // namespace
@@ -442,13 +493,11 @@ extern "C" int n2v_sgns_train(const int32_t* walks, int64_t n_walks, int32_t len
   const int nv = (P->dim + 127) / 128;
   cudaError_t err;
   const bool atomic = P->atomic_updates != 0;
-  // negative-row prefetch variant: OFF by default.  Measured on configs[2] (tables 2 x 0.54 GB, 70 % L2 hits):
-  // 5199 vs 5120 ms per epoch -- the kernel is bound by the row gather + reduction rate, not by the latency
-  // of the dependent target loop (profiles/README.md).  N2V_SGNS_PREFETCH=1 selects it (tests, tuning).
-  bool prefetch = false;
-  if (const char* e = getenv("N2V_SGNS_PREFETCH")) prefetch = e[0] == '1';
-  prefetch = prefetch && P->negative <= 32;
-#define N2V_SGNS_LAUNCH(NVV) err = launch<NVV>(A, atomic, prefetch, grid, smem, stream)
+  // latency-hiding mode (see sgns_kernel): N2V_SGNS_MODE=0..3 overrides the default (tests, tuning)
+  int mode = kDefaultMode;
+  if (const char* e = getenv("N2V_SGNS_MODE")) mode = atoi(e);
+  if (mode < 0 || mode > 3 || P->negative > 32) mode = 0;
+#define N2V_SGNS_LAUNCH(NVV) err = launch<NVV>(A, atomic, mode, grid, smem, stream)
   if (nv <= 1) N2V_SGNS_LAUNCH(1);
   else if (nv <= 2) N2V_SGNS_LAUNCH(2);
   else if (nv <= 4) N2V_SGNS_LAUNCH(4);

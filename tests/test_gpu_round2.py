@@ -393,31 +393,38 @@ def test_data_parallel_averaging_auc_band(n2v):
         assert auc[G] >= auc[1] - 0.01 and abs(auc[G] - auc[1]) <= 0.035, auc
 
 
-@pytest.mark.parametrize("dim,K", [(128, 5), (100, 5), (256, 7), (32, 1)])
-def test_sgns_negative_prefetch_variant_is_the_same_computation(n2v, monkeypatch, dim, K):
-    """The kernel variant used for tables beyond L2 draws a pair's K negatives up front and prefetches
-    their rows into L2; draws, targets and arithmetic are unchanged: in the deterministic single-warp
-    trace mode the pair trace and both tables are bit-identical to the plain variant's, and the
-    multi-warp kernels agree on the pair / token counts."""
+@pytest.mark.parametrize("dim,K", [(128, 5), (100, 5), (256, 7), (32, 1), (64, 32)])
+def test_sgns_latency_hiding_modes_are_the_same_computation(n2v, monkeypatch, dim, K):
+    """sgns_kernel MODE 1-3 (negatives drawn up front + L2 prefetch of their rows; lane-parallel draws
+    from the jumped-ahead PCG stream; double-buffered target rows) make the same draws and the same
+    arithmetic as MODE 0: in the deterministic single-warp trace mode the pair trace and both tables
+    are bit-identical, and the multi-warp kernels agree on the pair / token counts.  The corpus has
+    a 50-token head (repeated negatives inside a pair: the double-buffer hazard) and a 90k-id tail
+    (two-level negative table: 4 draws per negative)."""
     torch = n2v.torch
     from node2vec_b200.sgns import Word2Vec
     gen = torch.Generator(device="cuda"); gen.manual_seed(dim)
-    walks = torch.randint(0, 90000, (300, 25), device="cuda", dtype=torch.int32, generator=gen)   # two-level negative table
+    walks = torch.randint(0, 90000, (300, 25), device="cuda", dtype=torch.int32, generator=gen)
     walks[:, ::3] = torch.randint(0, 50, (300, 9), device="cuda", dtype=torch.int32, generator=gen)
+    small = torch.randint(0, 12, (200, 25), device="cuda", dtype=torch.int32, generator=gen)       # single-level table, many repeats
     out = {}
-    for flag in ("0", "1"):
-        monkeypatch.setenv("N2V_SGNS_PREFETCH", flag)
-        m = Word2Vec(size=dim, sg=1, negative=K, window=5, min_count=1, iter=2, seed=5, sample=1e-3)
-        m.build_vocab(walks)
-        m.train(walks, trace_cap=400000)
-        trace, alphas = m.last_trace
-        full = Word2Vec(size=dim, sg=1, negative=K, window=5, min_count=1, iter=1, seed=5, sample=1e-3)
-        full.build_vocab(walks)
-        full.train(walks)
-        out[flag] = (m.syn0.clone(), m.syn1neg.clone(), trace.copy(), alphas.copy(), dict(m.train_stats),
-                     (full.train_stats["pairs"], full.train_stats["tokens_kept"]), bool(torch.isfinite(full.syn0).all()))
-    a, b = out["0"], out["1"]
-    assert a[4] == b[4] and a[4]["pairs"] > 1000
-    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
-    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
-    assert a[5] == b[5] and a[6] and b[6]
+    for mode in ("0", "1", "2", "3"):
+        monkeypatch.setenv("N2V_SGNS_MODE", mode)
+        res = []
+        for corpus in (walks, small):
+            m = Word2Vec(size=dim, sg=1, negative=K, window=5, min_count=1, iter=2, seed=5, sample=1e-3)
+            m.build_vocab(corpus)
+            m.train(corpus, trace_cap=400000)
+            trace, alphas = m.last_trace
+            full = Word2Vec(size=dim, sg=1, negative=K, window=5, min_count=1, iter=1, seed=5, sample=1e-3)
+            full.build_vocab(corpus)
+            full.train(corpus)
+            res.append((m.syn0.clone(), m.syn1neg.clone(), trace.copy(), alphas.copy(), dict(m.train_stats),
+                        (full.train_stats["pairs"], full.train_stats["tokens_kept"]), bool(torch.isfinite(full.syn0).all())))
+        out[mode] = res
+    for mode in ("1", "2", "3"):
+        for a, b in zip(out["0"], out[mode]):
+            assert a[4] == b[4] and a[4]["pairs"] > 1000, mode
+            assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]), mode
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), mode
+            assert a[5] == b[5] and a[6] and b[6], mode
