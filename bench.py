@@ -854,6 +854,35 @@ def bench_partitioned(args):
     log(f"[rank {rank}] walk {kernel_ms:.1f} ms/pass, {steps_per_pass / kernel_ms / 1e6:.2f} G steps/s on this rank, "
         f"{remote:.0%} remote hops")
 
+    # ---- informational: the same graph REPLICATED from the parts (PartitionedGraph.localize: peers' arc records
+    # and hash sets copied over NVLink, 40 B/arc) -- what the product does when the graph fits beside the walk
+    # matrix; configs[4] names the partitioned form, so `value` above stays the peer-read walk
+    localized = None
+    if not args.no_localized:
+        sync_all()
+        t0 = time.perf_counter()
+        fits = g.localize()
+        sync_all()
+        t_copy = time.perf_counter() - t0
+        if fits:
+            k_loc = max(3, min(args.steps, 5))
+            check_rows = min(W, 200000)
+            ref_rows = out[:check_rows].clone()
+            ms_l = timed_walk(torch, g, start, nw, w, out, flush, k_loc, 3)
+            same = torch.tensor([1 if torch.equal(out[:check_rows], ref_rows) else 0], device=dev)
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            del ref_rows
+            tot_l = reduce_max(sum(ms_l))
+            localized = {"value": job_steps * k_loc / (tot_l * 1e-3), "unit": "walk-steps/s", "ms_per_step": tot_l / k_loc,
+                         "steps": k_loc, "copy_s": t_copy, "copied_bytes_per_gpu": int(sum(
+                             (a.numel() + h.numel()) * 4 for a, h in g._local_parts.values())),
+                         "same_walks_as_partitioned": bool(same.item()),
+                         "what": "PartitionedGraph.localize(): every rank copies its peers' arc records + hash sets over "
+                                 "NVLink and walks on local HBM only (replicated CSR assembled from the partitioned build)"}
+            log(f"[rank {rank}] localized walk {float(np.mean(ms_l)):.1f} ms/pass (copy {t_copy:.2f}s)")
+        else:
+            localized = {"unavailable": "the peers' parts do not fit beside the walk matrix on every rank"}
+
     # the graph is not needed any more: unmap the peers' parts and free this rank's (collective) before the
     # 2 x 34 GB tables are allocated
     n_arcs_total = int(g.n_arcs)
@@ -984,6 +1013,7 @@ def bench_partitioned(args):
                                         "tables_identical_across_ranks_after_averaging": parity_tables},
             "gpu_launches": args.steps + (sgns["gpu_launches"] if sgns else 0),
             "remote_hop_fraction": remote,
+            "walk_localized": localized,
             "e2e": {"value": job_steps / float(np.median(e2e_times)), "unit": "walk-steps/s",
                     "h2d_bytes_per_step": int(n_local_arcs * 8), "d2h_bytes_per_step": int(W * (L + 1) * 4),
                     "seconds": float(np.median(e2e_times)),
@@ -1021,6 +1051,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sgns", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-localized", action="store_true", help="N > 1: skip the replicated-from-parts walk block")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     world = int(os.environ.get("WORLD_SIZE", "1"))

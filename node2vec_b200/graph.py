@@ -476,6 +476,51 @@ class PartitionedGraph(DeviceGraph):
                 dist.barrier(group=group)
         return g
 
+    def localize(self, reserve_bytes: int = 0) -> bool:
+        """Turn the vertex-partitioned graph into a REPLICATED one assembled from the partitioned
+        build, when it fits: every rank copies its peers' arc records and hash sets (40 B per arc;
+        the peers' parts are already mapped here, so the copies are plain device-to-device
+        transfers over NVLink) and re-points ``parts[]`` to the copies.  The walk kernel is
+        unchanged -- same part-relative records, same results bit for bit -- but no gather
+        crosses NVLink any more ("a replicated CSR where it fits in 180 GB", BASELINE north_star).
+        ``col`` / ``weight`` (exact fallback only) stay remote.  Collective: every rank calls it;
+        returns False and changes nothing unless EVERY rank has room for the copies plus
+        ``reserve_bytes``."""
+        import torch.distributed as dist
+        if self.n_parts == 1 or getattr(self, "_local_parts", None):
+            return True
+        dev, G, rank = self.device, self.n_parts, self.rank
+        with torch.cuda.device(dev):
+            sizes = torch.zeros((G, 2), dtype=torch.int64, device=dev)
+            sizes[rank, 0], sizes[rank, 1] = int(self.arcs.shape[0]), int(self.hash.shape[0])
+            dist.all_reduce(sizes, group=self.group)
+            sizes = sizes.cpu().tolist()
+            need = sum((a + b) * 32 for p, (a, b) in enumerate(sizes) if p != rank)
+            torch.cuda.empty_cache()
+            free, _ = torch.cuda.mem_get_info(dev)
+            ok = torch.tensor([1 if free - need - int(reserve_bytes) > (2 << 30) else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                return False
+            local = {}
+            for p, (a, b) in enumerate(sizes):
+                if p == rank:
+                    continue
+                arcs = torch.empty((a, 8), dtype=torch.int32, device=dev)
+                hsh = torch.empty((b, 8), dtype=torch.int32, device=dev)
+                if a:
+                    arcs.copy_(torch.as_tensor(_RawBuffer(self._struct.parts[p].arcs, (a, 8), "<i4"), device=dev))
+                if b:
+                    hsh.copy_(torch.as_tensor(_RawBuffer(self._struct.parts[p].hash, (b, 8), "<i4"), device=dev))
+                local[p] = (arcs, hsh)
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)             # nobody frees a part a peer is still copying
+            for p, (arcs, hsh) in local.items():
+                self._struct.parts[p].arcs = arcs.data_ptr()
+                self._struct.parts[p].hash = hsh.data_ptr()
+            self._local_parts = local
+        return True
+
     def start_vertices(self) -> torch.Tensor:
         """This rank's start vertices (global ids): its own range, out-degree > 0."""
         own = self.vtx[self.v_lo:self.v_hi, 1]
@@ -496,6 +541,7 @@ class PartitionedGraph(DeviceGraph):
         if self.n_parts > 1 and dist.is_initialized():
             dist.barrier(group=self.group)
         self.arcs = self.col = self.weight = self.hash = None
+        self._local_parts = None
         for p in getattr(self, "_ipc_ptrs", []):
             if p:
                 lib.n2v_ipc_free(C.c_void_p(p))

@@ -63,6 +63,17 @@ def main():
         steps = start.numel() * 10 * 40
         print(f"[rank {rank}] {name}: OK, {remote:.0%} of hops land on a remote part; "
               f"partitioned {steps / t_part:.3e} steps/s vs replicated {steps / t_full:.3e}", flush=True)
+        if name == "unit symmetric":
+            # replicated-from-parts: peers' records copied over NVLink, same walks, no remote gathers
+            assert part.localize() is True
+            c, alive_c, st_c = part.walk(start, 4, 30, p, q, seed=11, collect_stats=True)
+            assert torch.equal(c, a) and torch.equal(alive_c, alive_a) and st_c["trials"] == st_a["trials"], name
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                part.walk(start, 10, 40, p, q, seed=1)
+            torch.cuda.synchronize()
+            print(f"[rank {rank}] {name}: localized {steps / ((time.perf_counter() - t0) / 3):.3e} steps/s", flush=True)
         dist.barrier()
         part.close()
         del full

@@ -105,3 +105,34 @@ def test_single_process_defaults():
     t = torch.ones(3)
     n2v_dist.average_tables((t,))
     assert t.tolist() == [1.0, 1.0, 1.0]
+
+
+def _rmat_worker(rank, world_size, port, out_dir):
+    """synth.rmat_partition_device on CPU tensors over gloo: every rank ends up with the arcs whose
+    source it owns, and the union is the graph a single process generates (strong scaling walks ONE
+    fixed graph whatever the number of ranks)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    try:
+        from node2vec_b200 import synth
+        src, dst = synth.rmat_partition_device(10, 8, rank, world_size, torch.device("cpu"))
+        S = (1024 + world_size - 1) // world_size
+        assert bool(((src >= rank * S) & (src < (rank + 1) * S)).all())
+        np.save(os.path.join(out_dir, f"arcs{rank}.npy"), np.stack([src.numpy(), dst.numpy()]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_rmat_is_the_same_graph_for_every_world_size(tmp_path):
+    from node2vec_b200 import synth
+    mp.spawn(_rmat_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    parts = [np.load(tmp_path / f"arcs{r}.npy") for r in range(2)]
+    got = np.concatenate(parts, axis=1)
+    one_s, one_d = synth.rmat_partition_device(10, 8, 0, 1, torch.device("cpu"))
+    want = np.stack([one_s.numpy(), one_d.numpy()])
+    assert got.shape == want.shape and np.array_equal(got, want)          # both sorted by (src, dst): rank ranges are ascending
+    key = got[0].astype(np.int64) << 32 | got[1]
+    assert len(np.unique(key)) == len(key) and (got[0] != got[1]).all()   # simple, loop-free
+    rev = got[1].astype(np.int64) << 32 | got[0]
+    assert np.array_equal(np.sort(rev), np.sort(key))                     # symmetric
