@@ -493,8 +493,11 @@ extern "C" int n2v_sgns_train(const int32_t* walks, int64_t n_walks, int32_t len
   const int nv = (P->dim + 127) / 128;
   cudaError_t err;
   const bool atomic = P->atomic_updates != 0;
-  // latency-hiding mode (see sgns_kernel): N2V_SGNS_MODE=0..3 overrides the default (tests, tuning)
-  int mode = kDefaultMode;
+  // latency-hiding mode (see sgns_kernel).  Tables beyond L2: mode 2 (lane-parallel negative draws + L2
+  // prefetch of their rows), measured 1.21x (configs[2], D = 128), 1.15x (D = 256), 1.43x (16 M-row tables)
+  // over mode 0; modes 1 and 3 are slower than 2 (profiles/r02_sgns_modes.txt).  L2-resident tables are
+  // issue-bound and keep mode 0.  N2V_SGNS_MODE=0..3 overrides (tests, tuning).
+  int mode = 2.0 * static_cast<double>(n_vertices) * P->dim * 4.0 > 96.0e6 ? 2 : kDefaultMode;
   if (const char* e = getenv("N2V_SGNS_MODE")) mode = atoi(e);
   if (mode < 0 || mode > 3 || P->negative > 32) mode = 0;
 #define N2V_SGNS_LAUNCH(NVV) err = launch<NVV>(A, atomic, mode, grid, smem, stream)

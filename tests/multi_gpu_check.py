@@ -104,6 +104,29 @@ def main():
     tot = torch.tensor([m.train_stats["pairs"]], device=dev)
     dist.all_reduce(tot)
     assert len(m.wv.index2word) > 0 and int(tot.item()) > 0
+    # link-prediction quality of the REAL data-parallel run (tables averaged by NCCL every epoch) against one
+    # GPU training on all the walks: AUC(G) >= AUC(1) - 0.01 and |AUC(G) - AUC(1)| <= 0.035 (parity gates)
+    from node2vec_b200 import workflows as wf
+    rng = np.random.default_rng(7)
+    n, blocks = 3000, 20
+    iu, ju = np.triu_indices(n, 1)
+    same = (iu // (n // blocks)) == (ju // (n // blocks))
+    keep = rng.random(len(iu)) < np.where(same, 0.06, 0.001)
+    ea, eb = torch.as_tensor(iu[keep], device=dev), torch.as_tensor(ju[keep], device=dev)
+    ta, tb, pos, neg = wf.split_edges(ea, eb, n, 0.1, seed=0)
+    sg = DeviceGraph.from_arcs(torch.cat([ta, tb]).int(), torch.cat([tb, ta]).int(), None, n_vertices=n)
+    all_walks, _, _ = sg.walk(sg.start_vertices(), 10, 40, 1.0, 1.0, seed=5)
+    mine_w = all_walks[all_walks.shape[0] * rank // world: all_walks.shape[0] * (rank + 1) // world].contiguous()
+    dp = Word2Vec(size=64, sg=1, negative=5, window=5, min_count=1, iter=5, seed=1, batch_words=10000,
+                  process_group=dist.group.WORLD)
+    dp.build_vocab(mine_w)
+    dp.train(mine_w)
+    one = Word2Vec(size=64, sg=1, negative=5, window=5, min_count=1, iter=5, seed=1, batch_words=10000)
+    one.build_vocab(all_walks)
+    one.train(all_walks)
+    auc_dp, auc_one = wf.link_auc(dp.syn0, pos, neg), wf.link_auc(one.syn0, pos, neg)
+    print(f"[rank {rank}] data-parallel AUC {auc_dp:.4f} vs single-GPU {auc_one:.4f}", flush=True)
+    assert auc_one > 0.75 and auc_dp >= auc_one - 0.01 and abs(auc_dp - auc_one) <= 0.035, (auc_dp, auc_one)
     dist.barrier()
     if rank == 0:
         print("MULTI_GPU_CHECK OK", flush=True)
