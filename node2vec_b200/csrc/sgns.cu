@@ -98,6 +98,20 @@ __device__ __forceinline__ float dot_rows(const Row<NV>& a, const Row<NV>& b) {
   return p;
 }
 
+// per-lane part of dot_rows (same FMA order), without the butterfly
+template <int NV>
+__device__ __forceinline__ float dot_partial(const Row<NV>& a, const Row<NV>& b) {
+  float p = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    p = fmaf(a.v[i].x, b.v[i].x, p);
+    p = fmaf(a.v[i].y, b.v[i].y, p);
+    p = fmaf(a.v[i].z, b.v[i].z, p);
+    p = fmaf(a.v[i].w, b.v[i].w, p);
+  }
+  return p;
+}
+
 // acc += g * x
 template <int NV>
 __device__ __forceinline__ void axpy(Row<NV>& acc, float g, const Row<NV>& x) {
@@ -188,8 +202,14 @@ __device__ __forceinline__ int32_t draw_negative(const SgnsArgs& A, uint32_t& rn
 //      LCG state after n steps is s * a^n + c * (a^n - 1) / (a - 1)): the K alias-entry gathers become ONE
 //      warp-wide gather instead of K dependent ones
 //   3  as 2, and the next target row is loaded while the current one is processed (double buffering)
+//   4  as 2 without the prefetch, and -- for K == 5 distinct targets -- all K rows are loaded at once into
+//      registers (K row gathers in flight instead of a chain of K), their K dot products reduced by K
+//      interleaved butterflies, then applied in the sequential order (positive, then negatives 0..K-1):
+//      identical floating-point results; a pair with a repeated target takes the one-by-one loop
+constexpr int kBatchK = 5;
 template <int NV, bool ATOMIC, bool TRACE, bool FULL, int MODE>
-__global__ void __launch_bounds__(kBlock, NV == 1 ? N2V_SGNS_MIN_BLOCKS : (NV == 2 ? N2V_SGNS_MIN_BLOCKS_NV2 : 1))
+__global__ void __launch_bounds__(kBlock, MODE == 4 ? (NV == 1 ? 3 : 2)
+                                                    : NV == 1 ? N2V_SGNS_MIN_BLOCKS : (NV == 2 ? N2V_SGNS_MIN_BLOCKS_NV2 : 1))
 sgns_kernel(const __grid_constant__ SgnsArgs A) {
   extern __shared__ int32_t smem[];
   __shared__ float exp_table[kExpTable];
@@ -297,7 +317,7 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
             rnd = rnd * kA + kC;                              // past all K negatives
           }
           const int lines = (A.dim * 4 + 127) >> 7;          // 128-byte lines per row
-          for (int first = 0; first < K * lines; first += 32) {
+          for (int first = 0; MODE != 4 && first < K * lines; first += 32) {
             const int idx = first + lane;
             const int d = min(idx / lines, K - 1);
             const int32_t t = __shfl_sync(0xffffffffu, my_tgt, d);
@@ -309,6 +329,19 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
           if (j + 1 < j1 && lane < lines) {                  // next context row of this centre (skips i itself)
             const int jn = (j + 1 == i) ? j + 2 : j + 1;
             if (jn < j1) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.syn0 + static_cast<int64_t>(sent[jn]) * A.dim + lane * 32));
+          }
+        }
+        // MODE 4: the K target rows, all in flight at once (only when the K targets are distinct)
+        Row<NV> rows[MODE == 4 ? kBatchK : 1];
+        bool batched = false;
+        if (MODE == 4) {
+          const unsigned same = __match_any_sync(0xffffffffu, lane < K ? my_tgt : -1 - lane);
+          batched = K == kBatchK && !__any_sync(0xffffffffu, lane < K && __popc(same) > 1);
+          if (batched) {
+#pragma unroll
+            for (int d = 0; d < kBatchK; ++d)
+              rows[d] = load_row<NV, FULL>(A.syn1neg + static_cast<int64_t>(__shfl_sync(0xffffffffu, my_tgt, d)) * A.dim,
+                                           A.dim, lane);
           }
         }
         const Row<NV> in = load_row<NV, FULL>(in_ptr, A.dim, lane);
@@ -331,6 +364,32 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
           axpy<NV>(pos, g, in);
           if (ATOMIC) axpy<NV>(pos_delta, g, in);
         }
+        if (MODE == 4 && batched) {
+          float f[kBatchK];
+#pragma unroll
+          for (int d = 0; d < kBatchK; ++d) f[d] = dot_partial<NV>(in, rows[d]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int d = 0; d < kBatchK; ++d) f[d] += __shfl_xor_sync(0xffffffffu, f[d], o);
+          }
+#pragma unroll
+          for (int d = 0; d < kBatchK; ++d) {
+            const int32_t tgt = __shfl_sync(0xffffffffu, my_tgt, d);
+            const bool skip = tgt == wi;
+            if (TRACE && trow && lane == 0) trow[2 + d] = skip ? -1 : tgt;
+            const bool in_range = f[d] > -kMaxExp && f[d] < kMaxExp;
+            const bool ok = in_range && !skip;
+            const float g = gradient(exp_table, f[d], 0.0f, alpha, ok);
+            if (TRACE) {
+              c_negskip += skip ? 1u : 0u;
+              c_clip += (!skip && !in_range) ? 1u : 0u;
+            }
+            axpy<NV>(work, g, rows[d]);
+            float* t_ptr = A.syn1neg + static_cast<int64_t>(tgt) * A.dim;
+            if (ATOMIC || ok) update_row<NV, ATOMIC, FULL>(t_ptr, A.dim, lane, g, in, rows[d]);
+          }
+        }
         // the K negative targets, in order (drawn at the top of the pair when MODE >= 1, else one by one here)
         Row<NV> ahead;                                        // MODE 3: row of the NEXT target, loaded early
         int32_t tgt_ahead = 0;
@@ -338,7 +397,7 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
           tgt_ahead = __shfl_sync(0xffffffffu, my_tgt, 0);
           ahead = load_row<NV, FULL>(A.syn1neg + static_cast<int64_t>(tgt_ahead) * A.dim, A.dim, lane);
         }
-        for (int d = 0; d < K; ++d) {
+        for (int d = 0; d < (MODE == 4 && batched ? 0 : K); ++d) {
           const int32_t tgt = MODE == 3 ? tgt_ahead : MODE >= 1 ? __shfl_sync(0xffffffffu, my_tgt, d) : draw_negative(A, rnd);
           const bool skip = tgt == wi;                      // gensim: a negative equal to the centre is skipped
           if (TRACE && trow && lane == 0) trow[2 + d] = skip ? -1 : tgt;
@@ -417,6 +476,8 @@ cudaError_t launch_mode(const SgnsArgs& A, bool atomic, int mode, int grid, size
     case 1: return launch_full<NV, FULL, 1>(A, atomic, grid, smem, stream);
     case 2: return launch_full<NV, FULL, 2>(A, atomic, grid, smem, stream);
     case 3: return launch_full<NV, FULL, 3>(A, atomic, grid, smem, stream);
+    case 4: return NV <= 2 ? launch_full<NV, FULL, (NV <= 2 ? 4 : 2)>(A, atomic, grid, smem, stream)
+                           : launch_full<NV, FULL, 2>(A, atomic, grid, smem, stream);
     default: return launch_full<NV, FULL, 0>(A, atomic, grid, smem, stream);
   }
 }
@@ -499,7 +560,7 @@ extern "C" int n2v_sgns_train(const int32_t* walks, int64_t n_walks, int32_t len
   // issue-bound and keep mode 0.  N2V_SGNS_MODE=0..3 overrides (tests, tuning).
   int mode = 2.0 * static_cast<double>(n_vertices) * P->dim * 4.0 > 96.0e6 ? 2 : kDefaultMode;
   if (const char* e = getenv("N2V_SGNS_MODE")) mode = atoi(e);
-  if (mode < 0 || mode > 3 || P->negative > 32) mode = 0;
+  if (mode < 0 || mode > 4 || P->negative > 32) mode = 0;
 #define N2V_SGNS_LAUNCH(NVV) err = launch<NVV>(A, atomic, mode, grid, smem, stream)
   if (nv <= 1) N2V_SGNS_LAUNCH(1);
   else if (nv <= 2) N2V_SGNS_LAUNCH(2);

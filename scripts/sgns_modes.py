@@ -14,11 +14,12 @@ from node2vec_b200.graph import DeviceGraph
 from node2vec_b200.sgns import Word2Vec
 
 dev = torch.device("cuda", 0)
+MODES = tuple(int(x) for x in os.environ.get("N2V_MODES", "0,1,2,3,4").split(","))
 
 
 def time_modes(name, walks, dims):
     for dim in dims:
-        for mode in (0, 1, 2, 3):
+        for mode in MODES:
             os.environ["N2V_SGNS_MODE"] = str(mode)
             m = Word2Vec(size=dim, sg=1, iter=3, seed=1, batch_words=10000, **bench.SGNS_HP)
             m.build_vocab(walks)
@@ -35,6 +36,13 @@ def time_modes(name, walks, dims):
             torch.cuda.empty_cache()
 
 
+w2 = bench.WORKLOADS["blogcatalog_like"]
+s2, d2 = bench.make_graph_host("blogcatalog_like")
+g = DeviceGraph.from_arcs(s2, d2, None, n_vertices=w2["n"])
+walks, alive, _ = g.walk(g.start_vertices(), w2["num_walks"], w2["walk_length"], w2["p"], w2["q"], seed=42)
+del g
+time_modes("blogcat", walks, (128,))
+del walks
 w = bench.WORKLOADS["rmat20"]
 src, dst = bench.config3_arcs_device(w, dev)
 g = DeviceGraph.from_arcs(src, dst, None, n_vertices=w["n"])
