@@ -554,11 +554,13 @@ extern "C" int n2v_sgns_train(const int32_t* walks, int64_t n_walks, int32_t len
   const int nv = (P->dim + 127) / 128;
   cudaError_t err;
   const bool atomic = P->atomic_updates != 0;
-  // latency-hiding mode (see sgns_kernel).  Tables beyond L2: mode 2 (lane-parallel negative draws + L2
-  // prefetch of their rows), measured 1.21x (configs[2], D = 128), 1.15x (D = 256), 1.43x (16 M-row tables)
-  // over mode 0; modes 1 and 3 are slower than 2 (profiles/r02_sgns_modes.txt).  L2-resident tables are
-  // issue-bound and keep mode 0.  N2V_SGNS_MODE=0..3 overrides (tests, tuning).
-  int mode = 2.0 * static_cast<double>(n_vertices) * P->dim * 4.0 > 96.0e6 ? 2 : kDefaultMode;
+  // latency-hiding mode (see sgns_kernel), chosen by measurement (profiles/r02_sgns_modes.txt, ms per epoch
+  // for modes 0 / 2 / 4): configs[1] tables 10 MB 144.9 / 152.9 / 140.2; configs[2] 1.07 GB 5109 / 4250 /
+  // 4117 (D = 256: 9142 / 7925 / 7283); 16 M-row tables 17 GB 6552 / 4611 / 4761.  So: K = 5 and D <= 256
+  // and tables <= 4 GB -> mode 4 (all K rows in flight); larger tables -> mode 2 (lane-parallel draws +
+  // L2 prefetch); otherwise L2-resident tables keep mode 0.  N2V_SGNS_MODE=0..4 overrides (tests, tuning).
+  const double table_bytes = 2.0 * static_cast<double>(n_vertices) * P->dim * 4.0;
+  int mode = (P->negative == kBatchK && P->dim <= 256 && table_bytes <= 4.0e9) ? 4 : table_bytes > 96.0e6 ? 2 : kDefaultMode;
   if (const char* e = getenv("N2V_SGNS_MODE")) mode = atoi(e);
   if (mode < 0 || mode > 4 || P->negative > 32) mode = 0;
 #define N2V_SGNS_LAUNCH(NVV) err = launch<NVV>(A, atomic, mode, grid, smem, stream)
