@@ -473,6 +473,46 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_AFFINITY0 = None
+
+
+def pin_to_gpu_numa(index):
+    """Run this process on the cores NVML reports as local to GPU `index` (its NUMA node) before any
+    pinned host buffer is allocated: host<->device copies then stay on the GPU's own root complex
+    (round-1 review: eight ranks sharing one node's PCIe path bent the end-to-end curve).  Best effort:
+    silently does nothing where NVML or sched_setaffinity is unavailable or the set would be empty."""
+    global _AFFINITY0
+    try:
+        import pynvml
+        if _AFFINITY0 is None:
+            _AFFINITY0 = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        try:                   # NVML numbers physical devices; CUDA_VISIBLE_DEVICES may have remapped `index`
+            import torch
+            pr = torch.cuda.get_device_properties(int(index))
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(b"%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id))
+        except Exception:  # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (wd >> b) & 1} & set(_AFFINITY0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
+def unpin():
+    """Give the CPU legs (one process per core) the original affinity back."""
+    if _AFFINITY0 is not None:
+        try:
+            os.sched_setaffinity(0, _AFFINITY0)
+        except OSError:
+            pass
+
+
 # ======================================================================================
 # single GPU: replicated graph
 # ======================================================================================
@@ -642,6 +682,7 @@ def bench_single(args):
     import torch
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
+    numa_cpus = pin_to_gpu_numa(0)
     name = args.workload
     w = WORKLOADS[name]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
@@ -674,7 +715,8 @@ def bench_single(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": walk["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": workload_config(name, w, 1),
-        "detail": {**walk["graph"], "sharding": "one GPU, replicated CSR"},
+        "detail": {**walk["graph"], "sharding": "one GPU, replicated CSR",
+                   "host_cores_used_for_e2e": len(numa_cpus) if numa_cpus else None},
         "gpu_launches": walk["gpu_launches"] + (sgns["gpu_launches"] if sgns else 0),
         "e2e": walk["e2e"], "roofline": walk["roofline"], "clocks": clocks.summary(), "walk_stats": walk["walk_stats"],
     }
@@ -703,6 +745,7 @@ def bench_single(args):
         b2.pop("gpu_launches")
         line["secondary"] = b2
         del walks2, host2
+    unpin()
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_walk(name, host_graph)
         line["cpu_baseline_c"] = cpu_baseline_walk_c(name, host_graph)
@@ -760,6 +803,7 @@ def bench_partitioned(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    pin_to_gpu_numa(local_rank)
     dist.init_process_group("nccl", device_id=dev)
     from node2vec_b200 import fugue, synth
     from node2vec_b200.embedding import Node2VecGensim
