@@ -428,3 +428,41 @@ def test_sgns_latency_hiding_modes_are_the_same_computation(n2v, monkeypatch, di
             assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]), mode
             assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), mode
             assert a[5] == b[5] and a[6] and b[6], mode
+
+
+def test_transition_categories_at_a_giant_hub(n2v):
+    """BASELINE configs[2] graph (reference order trim -> mirror: hubs of degree > 100000): walkers that
+    arrive at the largest hub v from a low-degree neighbour t choose x == t / x in N(t) / x elsewhere
+    with the reference's masses 1/p : |N(t) & N(v)| : (deg v - 1 - |N(t) & N(v)|)/q
+    (randomwalk.py:223-230) -- the mixture sampler's fp32 component thresholds at deg(v) ~ 2e5."""
+    torch = n2v.torch
+    src, dst = n2v.synth.rmat_hotspot_edges_device(20, 16, seed=42, hotspots=16, hotspot_degree=1 << 18)
+    (src, dst), _ = n2v.fugue.trim_index(None, (src, dst), indexed=True, directed=False, max_out_deg=10000, random_seed=1)
+    g = n2v.graph.DeviceGraph.from_arcs(src, dst, None, n_vertices=1 << 20)
+    assert g.flags & 7 == 7
+    deg = g.degrees().long()
+    v = int(torch.argmax(deg))
+    assert int(deg[v]) > 100000
+    base = g.vtx[:, 0].long()
+    nv = g.col[int(base[v]): int(base[v]) + int(deg[v])].long()
+    # t: a neighbour of v with a small degree that shares at least one neighbour with v
+    cand = nv[(deg[nv] >= 3) & (deg[nv] <= 12)][:200]
+    best = None
+    for t in cand.tolist():
+        nt = g.col[int(base[t]): int(base[t]) + int(deg[t])].long()
+        c = int(torch.isin(nt, nv).sum())
+        if c >= 1:
+            best = (t, nt, c)
+            break
+    assert best is not None
+    t, nt, c = best
+    for p, q in ((0.25, 4.0), (4.0, 2.0), (1.0, 8.0)):
+        ws, al, _ = g.walk(torch.tensor([t], dtype=torch.int32, device="cuda"), 3_000_000, 2, p, q, seed=77)
+        x = ws[al & (ws[:, 1] == v)][:, 2].long()
+        n = int(x.numel())
+        assert n > 100000
+        got = np.array([int((x == t).sum()), int((torch.isin(x, nt) & (x != t)).sum()), 0], dtype=np.float64)
+        got[2] = n - got[0] - got[1]
+        mass = np.array([1.0 / p, float(c), (int(deg[v]) - 1 - c) / q])
+        ok, pval = chi_square_ok(got, mass / mass.sum(), ALPHA)
+        assert ok, (p, q, t, v, int(deg[v]), c, got.tolist(), (mass / mass.sum() * n).tolist(), pval)
