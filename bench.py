@@ -716,6 +716,9 @@ def bench_single(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": workload_config(name, w, 1),
         "detail": {**walk["graph"], "sharding": "one GPU, replicated CSR",
+                   "note": "the N = 1 line is configs[2] (the largest configuration quoted on one B200); --gpus N > 1 runs "
+                           "configs[4] (RMAT-26, vertex-partitioned, strong scaling over N = 2/4/8): compare N >= 2 lines "
+                           "with each other, not with this one",
                    "host_cores_used_for_e2e": len(numa_cpus) if numa_cpus else None},
         "gpu_launches": walk["gpu_launches"] + (sgns["gpu_launches"] if sgns else 0),
         "e2e": walk["e2e"], "roofline": walk["roofline"], "clocks": clocks.summary(), "walk_stats": walk["walk_stats"],
