@@ -194,6 +194,32 @@ __device__ __forceinline__ int32_t draw_negative(const SgnsArgs& A, uint32_t& rn
   return (u2 < static_cast<uint32_t>(e.x)) ? static_cast<int32_t>(slot) : e.y;
 }
 
+// draw_negative split in two so that the alias-entry gather can stay in flight: `issue` consumes the draws
+// and starts the gather, `resolve` (first use of the loaded entry) picks slot or alias
+struct PendingNegative {
+  int2 entry;
+  uint32_t slot, u2;
+};
+__device__ __forceinline__ PendingNegative issue_negative(const SgnsArgs& A, uint32_t& rnd) {
+  uint32_t lo = 0, span = A.n_vertices;
+  if (A.n_top) {
+    const uint32_t c0 = __umulhi(pcg_next(rnd), A.n_top);
+    const int2 te = __ldg(A.neg_table + A.n_vertices + c0);
+    const uint32_t c = (pcg_next(rnd) < static_cast<uint32_t>(te.x)) ? c0 : static_cast<uint32_t>(te.y);
+    lo = c * N2V_NEG_CHUNK;
+    span = min(static_cast<uint32_t>(N2V_NEG_CHUNK), A.n_vertices - lo);
+  }
+  PendingNegative p;
+  const uint32_t u1 = pcg_next(rnd);
+  p.u2 = pcg_next(rnd);
+  p.slot = lo + __umulhi(u1, span);
+  p.entry = __ldg(A.neg_table + p.slot);
+  return p;
+}
+__device__ __forceinline__ int32_t resolve_negative(const PendingNegative& p) {
+  return (p.u2 < static_cast<uint32_t>(p.entry.x)) ? static_cast<int32_t>(p.slot) : p.entry.y;
+}
+
 // MODE (latency hiding for tables beyond L2; every mode makes the same draws and the same arithmetic):
 //   0  one negative at a time: draw -> alias entry -> row -> update (2 dependent round trips per negative)
 //   1  the pair's K negatives drawn first (sequentially), their rows prefetched into L2 by one warp-wide
@@ -206,9 +232,12 @@ __device__ __forceinline__ int32_t draw_negative(const SgnsArgs& A, uint32_t& rn
 //      registers (K row gathers in flight instead of a chain of K), their K dot products reduced by K
 //      interleaved butterflies, then applied in the sequential order (positive, then negatives 0..K-1):
 //      identical floating-point results; a pair with a repeated target takes the one-by-one loop
+//   5  as 4, and the NEXT pair of the same centre is drawn one pair ahead (its position in the walk's stream
+//      is known: K * draws_per_negative further on): its alias gathers fly during this pair's arithmetic and
+//      its K rows are prefetched into L2 at the end of this pair
 constexpr int kBatchK = 5;
 template <int NV, bool ATOMIC, bool TRACE, bool FULL, int MODE>
-__global__ void __launch_bounds__(kBlock, MODE == 4 ? (NV == 1 ? 3 : 2)
+__global__ void __launch_bounds__(kBlock, MODE >= 4 ? (NV == 1 ? 3 : 2)
                                                     : NV == 1 ? N2V_SGNS_MIN_BLOCKS : (NV == 2 ? N2V_SGNS_MIN_BLOCKS_NV2 : 1))
 sgns_kernel(const __grid_constant__ SgnsArgs A) {
   extern __shared__ int32_t smem[];
@@ -295,6 +324,8 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
       Row<NV> pos_delta;
 #pragma unroll
       for (int q = 0; q < NV; ++q) pos_delta.v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int32_t tgt_lookahead = 0;          // MODE 5: lane d's target of the NEXT pair, drawn one pair ahead
+      bool have_lookahead = false;
       for (int j = j0; j < j1; ++j) {
         if (j == i) continue;
         const int32_t wj = sent[j];
@@ -311,13 +342,16 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
               const int32_t tgt = draw_negative(A, rnd);
               if (lane == d) my_tgt = tgt;
             }
+          } else if (MODE == 5 && have_lookahead) {
+            my_tgt = tgt_lookahead;                           // drawn during the previous pair
+            rnd = rnd * kA + kC;
           } else {
             uint32_t mine = rnd * jA + jC;                    // the stream at lane d's negative
             if (lane < K) my_tgt = draw_negative(A, mine);    // K alias gathers in one warp-wide load
             rnd = rnd * kA + kC;                              // past all K negatives
           }
           const int lines = (A.dim * 4 + 127) >> 7;          // 128-byte lines per row
-          for (int first = 0; MODE != 4 && first < K * lines; first += 32) {
+          for (int first = 0; MODE < 4 && first < K * lines; first += 32) {
             const int idx = first + lane;
             const int d = min(idx / lines, K - 1);
             const int32_t t = __shfl_sync(0xffffffffu, my_tgt, d);
@@ -331,10 +365,21 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
             if (jn < j1) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.syn0 + static_cast<int64_t>(sent[jn]) * A.dim + lane * 32));
           }
         }
-        // MODE 4: the K target rows, all in flight at once (only when the K targets are distinct)
-        Row<NV> rows[MODE == 4 ? kBatchK : 1];
+        // MODE 5: start the next pair's draws now (rnd already stands at the next pair's first draw)
+        PendingNegative pending;
+        pending.slot = 0; pending.u2 = 0; pending.entry = make_int2(0, 0);
+        if (MODE == 5) {
+          const int jn = (j + 1 == i) ? j + 2 : j + 1;
+          have_lookahead = jn < j1;
+          if (have_lookahead && lane < K) {
+            uint32_t mine = rnd * jA + jC;
+            pending = issue_negative(A, mine);
+          }
+        }
+        // MODE >= 4: the K target rows, all in flight at once (only when the K targets are distinct)
+        Row<NV> rows[MODE >= 4 ? kBatchK : 1];
         bool batched = false;
-        if (MODE == 4) {
+        if (MODE >= 4) {
           const unsigned same = __match_any_sync(0xffffffffu, lane < K ? my_tgt : -1 - lane);
           batched = K == kBatchK && !__any_sync(0xffffffffu, lane < K && __popc(same) > 1);
           if (batched) {
@@ -364,7 +409,7 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
           axpy<NV>(pos, g, in);
           if (ATOMIC) axpy<NV>(pos_delta, g, in);
         }
-        if (MODE == 4 && batched) {
+        if (MODE >= 4 && batched) {
           float f[kBatchK];
 #pragma unroll
           for (int d = 0; d < kBatchK; ++d) f[d] = dot_partial<NV>(in, rows[d]);
@@ -397,7 +442,7 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
           tgt_ahead = __shfl_sync(0xffffffffu, my_tgt, 0);
           ahead = load_row<NV, FULL>(A.syn1neg + static_cast<int64_t>(tgt_ahead) * A.dim, A.dim, lane);
         }
-        for (int d = 0; d < (MODE == 4 && batched ? 0 : K); ++d) {
+        for (int d = 0; d < (MODE >= 4 && batched ? 0 : K); ++d) {
           const int32_t tgt = MODE == 3 ? tgt_ahead : MODE >= 1 ? __shfl_sync(0xffffffffu, my_tgt, d) : draw_negative(A, rnd);
           const bool skip = tgt == wi;                      // gensim: a negative equal to the centre is skipped
           if (TRACE && trow && lane == 0) trow[2 + d] = skip ? -1 : tgt;
@@ -428,6 +473,19 @@ sgns_kernel(const __grid_constant__ SgnsArgs A) {
             ahead = load_row<NV, FULL>(t_ptr, A.dim, lane);
         }
         add_row<NV, ATOMIC, FULL>(in_ptr, A.dim, lane, work, in);
+        if (MODE == 5 && have_lookahead) {                   // the next pair's targets: resolve, prefetch their rows
+          tgt_lookahead = lane < K ? resolve_negative(pending) : 0;
+          const int lines = (A.dim * 4 + 127) >> 7;
+          for (int first = 0; first < K * lines; first += 32) {
+            const int idx = first + lane;
+            const int d = min(idx / lines, K - 1);
+            const int32_t t = __shfl_sync(0xffffffffu, tgt_lookahead, d);
+            if (idx < K * lines) {
+              const float* line = A.syn1neg + static_cast<int64_t>(t) * A.dim + (idx - d * lines) * 32;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+            }
+          }
+        }
         ++c_pairs;
         if (TRACE) ++trace_pos;
       }
@@ -477,6 +535,8 @@ cudaError_t launch_mode(const SgnsArgs& A, bool atomic, int mode, int grid, size
     case 2: return launch_full<NV, FULL, 2>(A, atomic, grid, smem, stream);
     case 3: return launch_full<NV, FULL, 3>(A, atomic, grid, smem, stream);
     case 4: return NV <= 2 ? launch_full<NV, FULL, (NV <= 2 ? 4 : 2)>(A, atomic, grid, smem, stream)
+                           : launch_full<NV, FULL, 2>(A, atomic, grid, smem, stream);
+    case 5: return NV <= 2 ? launch_full<NV, FULL, (NV <= 2 ? 5 : 2)>(A, atomic, grid, smem, stream)
                            : launch_full<NV, FULL, 2>(A, atomic, grid, smem, stream);
     default: return launch_full<NV, FULL, 0>(A, atomic, grid, smem, stream);
   }
@@ -562,7 +622,7 @@ extern "C" int n2v_sgns_train(const int32_t* walks, int64_t n_walks, int32_t len
   const double table_bytes = 2.0 * static_cast<double>(n_vertices) * P->dim * 4.0;
   int mode = (P->negative == kBatchK && P->dim <= 256 && table_bytes <= 4.0e9) ? 4 : table_bytes > 96.0e6 ? 2 : kDefaultMode;
   if (const char* e = getenv("N2V_SGNS_MODE")) mode = atoi(e);
-  if (mode < 0 || mode > 4 || P->negative > 32) mode = 0;
+  if (mode < 0 || mode > 5 || P->negative > 32) mode = 0;
 #define N2V_SGNS_LAUNCH(NVV) err = launch<NVV>(A, atomic, mode, grid, smem, stream)
   if (nv <= 1) N2V_SGNS_LAUNCH(1);
   else if (nv <= 2) N2V_SGNS_LAUNCH(2);

@@ -397,7 +397,7 @@ def test_data_parallel_averaging_auc_band(n2v):
 def test_sgns_latency_hiding_modes_are_the_same_computation(n2v, monkeypatch, dim, K):
     """sgns_kernel MODE 1-4 (negatives drawn up front + L2 prefetch of their rows; lane-parallel draws
     from the jumped-ahead PCG stream; double-buffered target rows; all K = 5 distinct target rows in
-    flight at once) make the same draws and the same arithmetic as MODE 0: in the deterministic single-warp trace mode the pair trace and both tables
+    flight at once; the next pair drawn one pair ahead) make the same draws and the same arithmetic as MODE 0: in the deterministic single-warp trace mode the pair trace and both tables
     are bit-identical, and the multi-warp kernels agree on the pair / token counts.  The corpus has
     a 50-token head (repeated negatives inside a pair: the double-buffer hazard) and a 90k-id tail
     (two-level negative table: 4 draws per negative)."""
@@ -408,7 +408,7 @@ def test_sgns_latency_hiding_modes_are_the_same_computation(n2v, monkeypatch, di
     walks[:, ::3] = torch.randint(0, 50, (300, 9), device="cuda", dtype=torch.int32, generator=gen)
     small = torch.randint(0, 12, (200, 25), device="cuda", dtype=torch.int32, generator=gen)       # single-level table, many repeats
     out = {}
-    for mode in ("0", "1", "2", "3", "4"):
+    for mode in ("0", "1", "2", "3", "4", "5"):
         monkeypatch.setenv("N2V_SGNS_MODE", mode)
         res = []
         for corpus in (walks, small):
@@ -422,7 +422,7 @@ def test_sgns_latency_hiding_modes_are_the_same_computation(n2v, monkeypatch, di
             res.append((m.syn0.clone(), m.syn1neg.clone(), trace.copy(), alphas.copy(), dict(m.train_stats),
                         (full.train_stats["pairs"], full.train_stats["tokens_kept"]), bool(torch.isfinite(full.syn0).all())))
         out[mode] = res
-    for mode in ("1", "2", "3", "4"):
+    for mode in ("1", "2", "3", "4", "5"):
         for a, b in zip(out["0"], out[mode]):
             assert a[4] == b[4] and a[4]["pairs"] > 1000, mode
             assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3]), mode
