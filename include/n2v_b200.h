@@ -282,6 +282,11 @@ int n2v_get_l2_fetch_granularity(void);
 int64_t n2v_first_occurrence_slots(int64_t n_rows);
 int n2v_first_occurrence(const int64_t* key0, const int64_t* key1, const int64_t* key2, int64_t n_rows,
                          uint32_t* table, int64_t n_slots, int64_t* first_out, void* stream);
+/* The same for STRING vertex names in Arrow layout (row i = data[offsets[i] .. offsets[i+1]), UTF-8 bytes,
+ * int64 offsets as in pyarrow's large_string): keys are compared byte for byte, so the name column of a
+ * frame goes to the device as it is -- no host-side factorisation of the 2E names. */
+int n2v_first_occurrence_bytes(const int64_t* offsets, const uint8_t* data, int64_t n_rows, uint32_t* table,
+                               int64_t n_slots, int64_t* first_out, void* stream);
 
 /* ---- K5: hotspot trimming, bit-exact with the reference's sampler ------------------------
  * Replaces trim_hotspot_vertices (randomwalk.py:238-262): a vertex with more than `cap` out-arcs

@@ -69,6 +69,7 @@ _SIGNATURES = {
     "n2v_get_l2_fetch_granularity": (C.c_int, []),
     "n2v_first_occurrence_slots": (C.c_int64, [C.c_int64]),
     "n2v_first_occurrence": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_int64, _P, _P]),
+    "n2v_first_occurrence_bytes": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int64, _P, _P]),
     "n2v_vocab_count": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P]),
     "n2v_sgns_prepare": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_double, C.c_double, _P, _P, _P,
                                    C.POINTER(C.c_int64), _P]),

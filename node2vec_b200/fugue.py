@@ -201,13 +201,20 @@ def trim_index(
     return Frame(df_res.reset_index(drop=True)), Frame(name_id)
 
 
-def _frame_name_keys(df: pd.DataFrame):
-    """int64 keys for the ``src`` / ``dst`` names of a frame: integer names as they are, any other
-    names (strings) by their rank among the sorted distinct names (equality- and order-preserving).
+def _frame_name_keys(df: pd.DataFrame, device=None):
+    """int64 keys for the ``src`` / ``dst`` names of a frame: integer names as they are; string names by
+    their rank among the sorted distinct names (equality- and order-preserving) -- found ON THE DEVICE
+    from the raw UTF-8 bytes (``preprocess.string_name_ranks``: K6 on an Arrow buffer, only the V distinct
+    names are sorted on the host); any other hashable names by a host ``factorize``.
     Returns (src_key, dst_key, uniques or None, name dtype), or None when the names cannot be ranked."""
     src, dst = df["src"].to_numpy(), df["dst"].to_numpy()
     if src.dtype.kind in "iu" and dst.dtype.kind in "iu" and src.dtype != np.uint64 and dst.dtype != np.uint64:
         return src.astype(np.int64), dst.astype(np.int64), None, (src.dtype if src.dtype == dst.dtype else object)
+    if device is not None:
+        from .preprocess import string_name_ranks
+        got = string_name_ranks(df["src"], df["dst"], device)
+        if got is not None:
+            return got[0], got[1], got[2], object
     try:
         codes, uniques = pd.factorize(np.concatenate([src.astype(object), dst.astype(object)]), sort=True)
     except TypeError:
@@ -224,11 +231,11 @@ def _index_graph_frame_on_device(df: pd.DataFrame, directed, max_out_deg=None, r
     device: they are replaced by ranks first and mapped back in the name table.
     Returns None when the names cannot be ranked (mixed types): the caller falls back to pandas."""
     from .preprocess import index_graph_device, trim_partitioned
-    keys = _frame_name_keys(df)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    keys = _frame_name_keys(df, dev)
     if keys is None:
         return None
     s_key, d_key, uniques, name_dtype = keys
-    dev = torch.device("cuda", torch.cuda.current_device())
     ts, td = torch.as_tensor(s_key, device=dev), torch.as_tensor(d_key, device=dev)
     tw = None
     if "weight" in df.columns:

@@ -120,6 +120,58 @@ def first_occurrence(*cols: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def first_occurrence_bytes(offsets: torch.Tensor, data: torch.Tensor) -> torch.Tensor:
+    """``first_occurrence`` for byte-string keys in Arrow layout (int64 ``offsets[n + 1]`` into the
+    uint8 ``data``): first[i] = the smallest j whose bytes equal row i's."""
+    lib = _lib.load()
+    n, dev = int(offsets.numel()) - 1, offsets.device
+    out = torch.empty(max(n, 0), dtype=torch.int64, device=dev)
+    if n <= 0:
+        return out
+    n_slots = int(lib.n2v_first_occurrence_slots(n))
+    with torch.cuda.device(dev):
+        table = torch.empty(n_slots, dtype=torch.int32, device=dev)
+        _lib.check(lib.n2v_first_occurrence_bytes(_lib.ptr(offsets.contiguous()), _lib.ptr(data.contiguous()), n,
+                                                  _lib.ptr(table), n_slots, _lib.ptr(out), _lib.current_stream_ptr()),
+                   "n2v_first_occurrence_bytes")
+    return out
+
+
+def string_name_ranks(src_names, dst_names, device):
+    """Order- and equality-preserving int64 codes for STRING vertex names without factorising the 2E
+    names on the host: the names go to the device as one Arrow ``large_string`` buffer pair, K6 finds
+    every name's first occurrence byte for byte, only the V DISTINCT names come back to be sorted
+    (Arrow's binary order = Python's ``str`` order), and the ranks are broadcast to the rows on the
+    device.  Returns (src_code, dst_code, sorted distinct names as an object array) or None when a
+    name is not a string / is missing (the caller falls back)."""
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    try:
+        arr = pa.concat_arrays([pa.array(src_names, type=pa.large_string()), pa.array(dst_names, type=pa.large_string())])
+    except (pa.ArrowInvalid, pa.ArrowTypeError, TypeError):
+        return None
+    if arr.null_count:
+        return None
+    n, e = len(arr), len(src_names)
+    bufs = arr.buffers()
+    offsets = np.frombuffer(bufs[1], dtype=np.int64)[arr.offset: arr.offset + n + 1]
+    data = np.frombuffer(bufs[2], dtype=np.uint8) if bufs[2] is not None and bufs[2].size else np.zeros(1, dtype=np.uint8)
+    t_off = torch.as_tensor(offsets.copy(), device=device)
+    t_dat = torch.as_tensor(data.copy(), device=device)
+    first = first_occurrence_bytes(t_off, t_dat)
+    is_first = first == torch.arange(n, device=device)
+    pos = torch.nonzero(is_first).view(-1)
+    distinct = arr.take(pa.array(pos.cpu().numpy()))                  # V names, first-occurrence order
+    order = pc.sort_indices(distinct).to_numpy()                       # binary (UTF-8) order = str order
+    rank = np.empty(len(order), dtype=np.int64)
+    rank[order] = np.arange(len(order), dtype=np.int64)
+    dense = torch.cumsum(is_first.to(torch.int64), 0) - 1              # index among the distinct names
+    code = torch.as_tensor(rank, device=device)[dense[first]]
+    uniques = distinct.take(pa.array(order)).to_numpy(zero_copy_only=False)
+    return code[:e].contiguous(), code[e:].contiguous(), uniques
+
+
 def _weight_key(w: torch.Tensor) -> torch.Tensor:
     """IEEE bit pattern with pandas' equality: -0.0 == 0.0 and every NaN equals every NaN."""
     w = w.double()

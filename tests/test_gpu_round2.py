@@ -466,3 +466,28 @@ def test_transition_categories_at_a_giant_hub(n2v):
         mass = np.array([1.0 / p, float(c), (int(deg[v]) - 1 - c) / q])
         ok, pval = chi_square_ok(got, mass / mass.sum(), ALPHA)
         assert ok, (p, q, t, v, int(deg[v]), c, got.tolist(), (mass / mass.sum() * n).tolist(), pval)
+
+
+def test_first_occurrence_on_string_names(n2v):
+    """n2v_first_occurrence_bytes: first occurrence of UTF-8 byte strings in Arrow layout (empty names,
+    shared prefixes, multi-byte characters, one very long name), and the rank codes built from it."""
+    import pandas as pd
+    import pyarrow as pa
+    torch = n2v.torch
+    from node2vec_b200 import preprocess
+    rng = np.random.default_rng(4)
+    pool = ["", "a", "aa", "aaa", "b", "ab", "ba", "é", "éa", "日本", "user_" + "x" * 300] + [f"v{i}" for i in range(400)]
+    names = [pool[i] for i in rng.integers(0, len(pool), 30000)]
+    arr = pa.array(names, type=pa.large_string())
+    off = np.frombuffer(arr.buffers()[1], dtype=np.int64)[: len(arr) + 1].copy()
+    dat = np.frombuffer(arr.buffers()[2], dtype=np.uint8).copy()
+    got = preprocess.first_occurrence_bytes(torch.as_tensor(off, device="cuda"), torch.as_tensor(dat, device="cuda")).cpu().numpy()
+    seen, want = {}, np.empty(len(names), dtype=np.int64)
+    for i, s in enumerate(names):
+        want[i] = seen.setdefault(s, i)
+    assert np.array_equal(got, want)
+    src, dst = pd.Series(names[:15000]), pd.Series(names[15000:])
+    s_code, d_code, uniques = preprocess.string_name_ranks(src, dst, torch.device("cuda"))
+    assert uniques.tolist() == sorted(set(names))
+    assert [uniques[c] for c in s_code.cpu().tolist()] == names[:15000] and [uniques[c] for c in d_code.cpu().tolist()] == names[15000:]
+    assert preprocess.string_name_ranks(pd.Series(["a", 1], dtype=object), pd.Series(["b", "c"]), torch.device("cuda")) is None
