@@ -14,10 +14,30 @@ inline int grid_for(int64_t n_warps_needed) {
   return static_cast<int>(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
-// One WARP per vertex: lanes clear the vertex's buckets, then insert its arcs in parallel with
-// atomicCAS.  Slots of a bucket fill in order (a lane moves to slot k+1 only after seeing slot k
-// taken) and buckets only ever fill up, so the final table satisfies the lookup invariant "x
-// lives in the first bucket of its probe sequence that had room" whatever the interleaving.
+// A vertex of kHubDeg arcs or more gets a whole 1024-thread CTA (fill_hub_buckets): one warp per
+// vertex left the 232k-arc hotspots of BASELINE configs[2] as a 7 ms tail of a 0.5 ms kernel.
+constexpr uint32_t kHubDeg = 2048;
+constexpr int kHubBlock = 1024;
+
+// Insert x into the table of a vertex with nb buckets.  Slots of a bucket fill in order (a thread
+// moves to slot k+1 only after seeing slot k taken) and buckets only ever fill up, so the final
+// table satisfies the lookup invariant "x lives in the first bucket of its probe sequence that had
+// room" whatever the interleaving of the inserting threads.
+__device__ __forceinline__ void insert_neighbour(int32_t* __restrict__ table, uint32_t nb, int32_t x) {
+  uint32_t b = __umulhi(static_cast<uint32_t>(x) * N2V_HASH_MULT, nb);
+  for (;;) {
+    int32_t* slot = table + b * N2V_HASH_SLOTS;
+    for (int k = 0; k < N2V_HASH_SLOTS; ++k) {
+      const int32_t old = atomicCAS(slot + k, N2V_HASH_EMPTY, x);
+      if (old == N2V_HASH_EMPTY || old == x) return;
+    }
+    b = (b + 1 == nb) ? 0 : b + 1;
+  }
+}
+
+// One WARP per vertex below kHubDeg: lanes clear the vertex's buckets, then insert its arcs in
+// parallel with atomicCAS.  Every vertex gets its hbase here; hubs get their table from
+// fill_hub_buckets.
 __global__ void fill_buckets(n2v_vertex_t* __restrict__ vtx, const int32_t* __restrict__ col,
                              int64_t n_vertices, int32_t* __restrict__ hash) {
   const int lane = threadIdx.x & 31;
@@ -27,7 +47,7 @@ __global__ void fill_buckets(n2v_vertex_t* __restrict__ vtx, const int32_t* __re
     const uint32_t deg = vtx[v].deg, base = vtx[v].base;
     const uint32_t hb = n2v_hash_base(base, static_cast<uint32_t>(v));
     if (lane == 0) vtx[v].hbase = hb;
-    if (deg == 0) continue;
+    if (deg == 0 || deg >= kHubDeg) continue;
     const uint32_t nb = n2v_hash_nbuckets(deg);
     int32_t* table = hash + static_cast<size_t>(hb) * N2V_HASH_SLOTS;
     for (uint32_t i = lane; i < nb * N2V_HASH_SLOTS; i += 32) table[i] = N2V_HASH_EMPTY;
@@ -36,18 +56,43 @@ __global__ void fill_buckets(n2v_vertex_t* __restrict__ vtx, const int32_t* __re
     for (uint32_t i = lane; i < deg; i += 32) {
       const int32_t x = c[i];
       if (i > 0 && c[i - 1] == x) continue;  // multi-arc: one entry per distinct neighbour (col is sorted)
-      uint32_t b = __umulhi(static_cast<uint32_t>(x) * N2V_HASH_MULT, nb);
-      bool done = false;
-      while (!done) {
-        int32_t* slot = table + b * N2V_HASH_SLOTS;
-        for (int k = 0; k < N2V_HASH_SLOTS && !done; ++k) {
-          const int32_t old = atomicCAS(slot + k, N2V_HASH_EMPTY, x);
-          done = (old == N2V_HASH_EMPTY) || (old == x);
-        }
-        b = (b + 1 == nb) ? 0 : b + 1;
-      }
+      insert_neighbour(table, nb, x);
     }
     __syncwarp();
+  }
+}
+
+// One CTA per hub: the CTAs stride over 1024-vertex tiles of the header array (one coalesced
+// pass), collect the tile's hubs in shared memory and build each hub's table with all threads.
+__global__ void __launch_bounds__(kHubBlock) fill_hub_buckets(const n2v_vertex_t* __restrict__ vtx,
+                                                              const int32_t* __restrict__ col, int64_t n_vertices,
+                                                              int32_t* __restrict__ hash) {
+  __shared__ int32_t hubs[kHubBlock];
+  __shared__ int n_hubs;
+  const int64_t n_tiles = (n_vertices + kHubBlock - 1) / kHubBlock;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t v0 = tile * kHubBlock + threadIdx.x;
+    const bool hub = v0 < n_vertices && vtx[v0].deg >= kHubDeg;
+    if (__syncthreads_count(hub) == 0) continue;
+    if (threadIdx.x == 0) n_hubs = 0;
+    __syncthreads();
+    if (hub) hubs[atomicAdd(&n_hubs, 1)] = threadIdx.x;
+    __syncthreads();
+    for (int h = 0; h < n_hubs; ++h) {
+      const int64_t v = tile * kHubBlock + hubs[h];
+      const uint32_t deg = vtx[v].deg, base = vtx[v].base;
+      const uint32_t nb = n2v_hash_nbuckets(deg);
+      int32_t* table = hash + static_cast<size_t>(n2v_hash_base(base, static_cast<uint32_t>(v))) * N2V_HASH_SLOTS;
+      for (uint32_t i = threadIdx.x; i < nb * N2V_HASH_SLOTS; i += kHubBlock) table[i] = N2V_HASH_EMPTY;
+      __syncthreads();
+      const int32_t* c = col + base;
+      for (uint32_t i = threadIdx.x; i < deg; i += kHubBlock) {
+        const int32_t x = c[i];
+        if (i > 0 && c[i - 1] == x) continue;
+        insert_neighbour(table, nb, x);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -67,6 +112,9 @@ extern "C" int n2v_hash_build(n2v_vertex_t* vtx, const int32_t* col, int64_t n_v
                 "n2v_hash_build: bucket capacity %lld out of range", static_cast<long long>(n_buckets_cap));
   N2V_CHECK_ARG((reinterpret_cast<uintptr_t>(hash) & 31) == 0, "n2v_hash_build: hash must be 32-byte aligned");
   fill_buckets<<<grid_for(n_vertices), kBlock, 0, stream>>>(vtx, col, n_vertices, hash);
+  const int64_t n_tiles = (n_vertices + kHubBlock - 1) / kHubBlock;
+  const int64_t hub_cap = int64_t(n2v::sm_count()) * 2;
+  fill_hub_buckets<<<static_cast<int>(n_tiles < hub_cap ? n_tiles : hub_cap), kHubBlock, 0, stream>>>(vtx, col, n_vertices, hash);
   N2V_LAUNCH_OK();
   return N2V_OK;
 }

@@ -44,6 +44,28 @@ inline int sm_count() {
   return cached;
 }
 
+// Small stream-ordered scratch (counters, hub lists).  The device's default memory pool hands every
+// free block back to the OS at the next synchronisation unless its release threshold is raised, and each
+// entry point that reads a counter back synchronises -- so every build paid a cuMemCreate / cuMemMap
+// round trip (milliseconds) for a few hundred KB.  Keep up to 64 MB cached per device instead (raised
+// once per host thread and device, never lowered).
+inline cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t stream) {
+  static thread_local int tuned_dev = -1;
+  int dev = 0;
+  const cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev != tuned_dev) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t cur = 0, want = 64ull << 20;
+      if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < want)
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &want);
+    }
+    tuned_dev = dev;
+  }
+  return cudaMallocAsync(p, bytes, stream);
+}
+
 // ---- 16-byte record loads (one LDG.128 each, read-only path) ------------------------
 // {base, deg, hbase, wsum-bits} of a vertex in one load
 __device__ __forceinline__ uint4 load_vtx(const n2v_vertex_t* p) {

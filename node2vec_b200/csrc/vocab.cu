@@ -284,7 +284,7 @@ extern "C" int n2v_vocab_count(const int32_t* walks, int64_t n_walks, int32_t le
   if (n_walks == 0) return N2V_OK;
   N2V_CHECK_ARG(walks && counts && first_pos, "n2v_vocab_count: NULL buffer");
   unsigned int* bad = nullptr;
-  N2V_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&bad), sizeof(unsigned int), stream));
+  N2V_CUDA(n2v::scratch_alloc(reinterpret_cast<void**>(&bad), sizeof(unsigned int), stream));
   N2V_CUDA(cudaMemsetAsync(bad, 0, sizeof(unsigned int), stream));
   count_tokens<<<grid_for(n_walks * len), kBlock, 0, stream>>>(walks, n_walks, len, pitch, n_vertices, pos_offset,
                                                               reinterpret_cast<unsigned long long*>(counts),
@@ -307,7 +307,7 @@ extern "C" int n2v_sgns_prepare(const int64_t* counts, int64_t n_vertices, int64
   N2V_CHECK_ARG(sample >= 0.0, "n2v_sgns_prepare: negative sample");
   double* probs = static_cast<double*>(scratch);   // count^ns_exponent per id
   unsigned long long* d_tot = nullptr;
-  N2V_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_tot), 4 * sizeof(unsigned long long), stream));
+  N2V_CUDA(n2v::scratch_alloc(reinterpret_cast<void**>(&d_tot), 4 * sizeof(unsigned long long), stream));
   N2V_CUDA(cudaMemsetAsync(d_tot, 0, 4 * sizeof(unsigned long long), stream));
   retain_totals<<<grid_for(n_vertices), kBlock, 0, stream>>>(counts, n_vertices, min_count, d_tot);
   N2V_LAUNCH_OK();

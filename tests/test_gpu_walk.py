@@ -128,6 +128,15 @@ def test_hash_sets_answer_membership_exactly(n2v):
             assert ok == (x in nbrs[t])
             probes += n; count += 1
     assert probes / count < 1.3
+    # the hub (one CTA per vertex above 2048 arcs) and a few warp-built vertices: the table holds exactly the
+    # distinct neighbours, each once, used slots contiguous from slot 0, and every member is found
+    for t in [11] + list(nbrs)[:20]:
+        nb = (int(h["deg"][t]) + 3) >> 2
+        rows = table[int(h["hbase"][t]): int(h["hbase"][t]) + nb]
+        used = rows != -1
+        assert (used[:, :-1] | ~used[:, 1:]).all()
+        assert sorted(rows[used].tolist()) == sorted(nbrs[t])
+        assert all(lookup(t, x)[0] for x in nbrs[t])
     assert np.array_equal(h["hbase"], ((h["base"].astype(np.int64) >> 2) + np.arange(len(h["deg"]))).astype(np.uint32))
 
 
