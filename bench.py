@@ -63,13 +63,25 @@ SEED = 42
 # ======================================================================================
 # graphs
 # ======================================================================================
-def config3_arcs_device(w, dev):
-    """configs[2] on the device: undirected edge list -> trim_index(trim, then symmetrise)."""
+def config3_arcs_device(w, dev, prep=None):
+    """configs[2] on the device: undirected edge list -> trim_index(trim, then symmetrise).
+    `prep` (a dict) receives the wall time of that trim_index call (not part of `value`)."""
+    import torch
     from node2vec_b200 import fugue, synth
     src, dst = synth.rmat_hotspot_edges_device(w["scale"], w["edge_factor"], seed=SEED, device=dev,
                                                hotspots=w["hotspots"], hotspot_degree=w["hotspot_degree"])
+    n_in = int(src.numel())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
     (src, dst), _ = fugue.trim_index(None, (src, dst), indexed=True, directed=False, max_out_deg=w["max_out_deg"],
                                      random_seed=1)
+    torch.cuda.synchronize()
+    if prep is not None:
+        prep.update({"trim_index_ms": round(1e3 * (time.perf_counter() - t0), 2), "edges_in": n_in,
+                     "arcs_out": int(src.numel()),
+                     "what": "fugue.trim_index(device arc tensors, indexed=True, directed=False, max_out_deg, "
+                             "random_seed): K5 seeded trimming (numpy-RandomState-exact) + K6 undirected expansion; "
+                             "first call, allocator cold"})
     return src.to(dev).contiguous(), dst.to(dev).contiguous()
 
 
@@ -687,8 +699,9 @@ def bench_single(args):
     w = WORKLOADS[name]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
     clocks = ClockSampler(0)
+    prep = {}
     if name == "rmat20":
-        src, dst = config3_arcs_device(w, dev)
+        src, dst = config3_arcs_device(w, dev, prep)
         level, note = "hbm", ("graph %.2f GB, tables 2 x %.2f GB: DRAM-resident; the walk is a stream of random 32-byte "
                               "sector gathers, so the HBM fraction by algorithmic bytes is bounded by the random-sector "
                               "ceiling (roofline.gather), not by the copy peak")
@@ -719,7 +732,8 @@ def bench_single(args):
                    "note": "the N = 1 line is configs[2] (the largest configuration quoted on one B200); --gpus N > 1 runs "
                            "configs[4] (RMAT-26, vertex-partitioned, strong scaling over N = 2/4/8): compare N >= 2 lines "
                            "with each other, not with this one",
-                   "host_cores_used_for_e2e": len(numa_cpus) if numa_cpus else None},
+                   "host_cores_used_for_e2e": len(numa_cpus) if numa_cpus else None,
+                   **({"prep": prep} if prep else {})},
         "gpu_launches": walk["gpu_launches"] + (sgns["gpu_launches"] if sgns else 0),
         "e2e": walk["e2e"], "roofline": walk["roofline"], "clocks": clocks.summary(), "walk_stats": walk["walk_stats"],
     }

@@ -645,6 +645,25 @@ def test_device_trim_bit_exact_with_reference_sampler(n2v):
         got = picked.cpu().numpy()
         for h, d in enumerate(degs):
             assert got[h].tolist() == np.random.RandomState(seed).permutation(d)[:cap].tolist(), (seed, cap, d)
+    # the WHOLE permutation (cap >= deg), from two elements to a BASELINE-configs[2] hotspot (2^18 arcs): every
+    # batch shape of the warp-parallel shuffle -- MT refill boundaries, clashing partners, the last few indices
+    degs = [2, 3, 5, 33, 624, 625, 1249, 20011, (1 << 18) + 1]
+    cap = max(degs)
+    deg = torch.as_tensor(degs, dtype=torch.int64, device="cuda")
+    off = torch.cumsum(deg, 0) - deg
+    for seed in (0, 1, 123456789):
+        scratch = torch.empty(int(deg.sum()), dtype=torch.int32, device="cuda")
+        picked = torch.full((len(degs), cap), -1, dtype=torch.int32, device="cuda")
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        n2v.lib.check(lib.n2v_trim_sample(n2v.lib.ptr(deg), n2v.lib.ptr(off), len(degs), cap, C.c_uint32(seed),
+                                          n2v.lib.ptr(scratch), n2v.lib.ptr(picked), n2v.lib.current_stream_ptr()))
+        t1.record()
+        got = picked.cpu().numpy()
+        print(f"n2v_trim_sample, largest vertex 2^18 + 1 arcs: {t0.elapsed_time(t1):.2f} ms")
+        for h, d in enumerate(degs):
+            assert np.array_equal(got[h, :d], np.random.RandomState(seed).permutation(d)), (seed, d)
+            assert (got[h, d:] == -1).all()
     # whole trim_index, tensor path vs pandas path (multi-arcs, weights, several hot vertices, untouched ones)
     rng = np.random.default_rng(8)
     src = np.concatenate([rng.integers(0, 40, 600), np.full(3000, 11), np.full(900, 3), np.full(901, 25)])
