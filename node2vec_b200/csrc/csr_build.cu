@@ -67,25 +67,41 @@ __global__ void close_runs(const uint64_t* __restrict__ keys, int64_t n, n2v_ver
   }
 }
 
-// SYMMETRIC: every arc (a,b,w) has a mirror (b,a,w).  Only meaningful on SIMPLE graphs.
+// SYMMETRIC: every arc (a,b,w) has a mirror (b,a,w).  Only meaningful on SIMPLE graphs (distinct arcs),
+// which is what makes a ONE-SIDED search exact: order the two ends of an arc by (degree, id); the arc
+// whose head is the smaller end is the pair's "searcher" and looks its mirror up in the head's row --
+// the SHORTER of the two rows, so an arc between a leaf and a 232k-arc hub costs a probe or two instead
+// of 18 -- and every other arc (self-loops aside) must be the mirror some searcher found.  Mirrors of
+// distinct searchers are distinct arcs, so "every search succeeded and #searchers == #others" means the
+// mirror map is a bijection.  balance accumulates #searchers - #others.
 __global__ void check_symmetric(const uint64_t* __restrict__ keys, const double* __restrict__ w_sorted,
                                 int64_t n, const n2v_vertex_t* __restrict__ vtx,
-                                unsigned int* __restrict__ not_flags, const unsigned int* __restrict__ bad_ids) {
+                                unsigned int* __restrict__ not_flags, const unsigned int* __restrict__ bad_ids,
+                                unsigned long long* __restrict__ balance) {
   if (*bad_ids) return;
   bool bad = false;
+  long long local = 0;
   for (int64_t i = blockIdx.x * int64_t(kBlock) + threadIdx.x; i < n; i += int64_t(gridDim.x) * kBlock) {
     const uint64_t k = keys[i];
     const uint32_t a = static_cast<uint32_t>(k >> 32), b = static_cast<uint32_t>(k);
+    if (a == b) continue;                              // a self-loop is its own mirror
+    const uint32_t deg_a = vtx[a].deg, deg_b = vtx[b].deg;
+    if (!(deg_b < deg_a || (deg_b == deg_a && b < a))) {
+      --local;                                         // to be found by its mirror
+      continue;
+    }
+    ++local;
     const uint64_t want = (static_cast<uint64_t>(b) << 32) | a;
     const uint64_t lo0 = vtx[b].base;
-    uint64_t lo = lo0, hi = lo0 + vtx[b].deg;
+    uint64_t lo = lo0, hi = lo0 + deg_b;
     while (lo < hi) {
       const uint64_t mid = (lo + hi) >> 1;
       if (keys[mid] < want) lo = mid + 1; else hi = mid;
     }
-    if (lo >= lo0 + vtx[b].deg || keys[lo] != want || w_sorted[lo] != w_sorted[i]) bad = true;
+    if (lo >= lo0 + deg_b || keys[lo] != want || w_sorted[lo] != w_sorted[i]) bad = true;
   }
   if (bad) atomicOr(not_flags, N2V_GRAPH_SYMMETRIC);
+  if (local) atomicAdd(balance, static_cast<unsigned long long>(local));
 }
 
 struct Layout {
@@ -166,16 +182,18 @@ extern "C" int n2v_csr_build(const int32_t* src, const int32_t* dst, const doubl
   close_runs<<<grid, kBlock, 0, stream>>>(dk.Current(), n_arcs, vtx, dflags);
   N2V_LAUNCH_OK();
   if (replicated) {
-    check_symmetric<<<grid, kBlock, 0, stream>>>(dk.Current(), weight_sorted, n_arcs, vtx, dflags + 1, dflags);
+    check_symmetric<<<grid, kBlock, 0, stream>>>(dk.Current(), weight_sorted, n_arcs, vtx, dflags + 1, dflags,
+                                                 reinterpret_cast<unsigned long long*>(dflags + 2));
     N2V_LAUNCH_OK();
   }
 
-  unsigned int h[2] = {0, 0};
+  unsigned int h[4] = {0, 0, 0, 0};                    // [0] bad ids, [1] NOT-flags, [2..3] searcher balance (u64)
   N2V_CUDA(cudaMemcpyAsync(h, dflags, sizeof(h), cudaMemcpyDeviceToHost, stream));
   N2V_CUDA(cudaStreamSynchronize(stream));
   N2V_CHECK_ARG(h[0] == 0, "n2v_csr_build: vertex id outside [0, %lld) / [0, %lld)",
                 static_cast<long long>(n_vertices), static_cast<long long>(n_dst_vertices));
   flags &= ~h[1];
+  if (h[2] != 0 || h[3] != 0) flags &= ~uint32_t(N2V_GRAPH_SYMMETRIC);   // an arc nobody's mirror search found
   if (!replicated) flags &= ~uint32_t(N2V_GRAPH_SYMMETRIC);
   if (!(flags & N2V_GRAPH_SIMPLE)) flags &= ~uint32_t(N2V_GRAPH_SYMMETRIC);
   if (flags_host) *flags_host = flags;

@@ -15,7 +15,7 @@ inline int grid_for(int64_t n_warps_needed) {
 }
 
 // A vertex of kHubDeg arcs or more gets a whole 1024-thread CTA (fill_hub_buckets): one warp per
-// vertex left the 232k-arc hotspots of BASELINE configs[2] as a 7 ms tail of a 0.5 ms kernel.
+// vertex left the 232k-arc hotspots of BASELINE configs[2] as a 20 ms tail of a sub-millisecond kernel.
 constexpr uint32_t kHubDeg = 2048;
 constexpr int kHubBlock = 1024;
 
@@ -36,10 +36,12 @@ __device__ __forceinline__ void insert_neighbour(int32_t* __restrict__ table, ui
 }
 
 // One WARP per vertex below kHubDeg: lanes clear the vertex's buckets, then insert its arcs in
-// parallel with atomicCAS.  Every vertex gets its hbase here; hubs get their table from
-// fill_hub_buckets.
+// parallel with atomicCAS.  Every vertex gets its hbase here; hubs are only LISTED (their ids cluster --
+// R-MAT's heavy vertices are the ids with few set bits -- so the list, not the id range, is what
+// fill_hub_buckets strides over).
 __global__ void fill_buckets(n2v_vertex_t* __restrict__ vtx, const int32_t* __restrict__ col,
-                             int64_t n_vertices, int32_t* __restrict__ hash) {
+                             int64_t n_vertices, int32_t* __restrict__ hash, int32_t* __restrict__ hubs,
+                             unsigned int* __restrict__ n_hubs) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * int64_t(kBlock) + threadIdx.x) >> 5;
   const int64_t n_warps = (int64_t(gridDim.x) * kBlock) >> 5;
@@ -47,7 +49,11 @@ __global__ void fill_buckets(n2v_vertex_t* __restrict__ vtx, const int32_t* __re
     const uint32_t deg = vtx[v].deg, base = vtx[v].base;
     const uint32_t hb = n2v_hash_base(base, static_cast<uint32_t>(v));
     if (lane == 0) vtx[v].hbase = hb;
-    if (deg == 0 || deg >= kHubDeg) continue;
+    if (deg == 0) continue;
+    if (deg >= kHubDeg) {
+      if (lane == 0) hubs[atomicAdd(n_hubs, 1u)] = static_cast<int32_t>(v);
+      continue;
+    }
     const uint32_t nb = n2v_hash_nbuckets(deg);
     int32_t* table = hash + static_cast<size_t>(hb) * N2V_HASH_SLOTS;
     for (uint32_t i = lane; i < nb * N2V_HASH_SLOTS; i += 32) table[i] = N2V_HASH_EMPTY;
@@ -62,37 +68,27 @@ __global__ void fill_buckets(n2v_vertex_t* __restrict__ vtx, const int32_t* __re
   }
 }
 
-// One CTA per hub: the CTAs stride over 1024-vertex tiles of the header array (one coalesced
-// pass), collect the tile's hubs in shared memory and build each hub's table with all threads.
+// One CTA per listed hub (the count stays on the device: the CTAs stride over the list and leave at
+// once when it is empty).
 __global__ void __launch_bounds__(kHubBlock) fill_hub_buckets(const n2v_vertex_t* __restrict__ vtx,
-                                                              const int32_t* __restrict__ col, int64_t n_vertices,
-                                                              int32_t* __restrict__ hash) {
-  __shared__ int32_t hubs[kHubBlock];
-  __shared__ int n_hubs;
-  const int64_t n_tiles = (n_vertices + kHubBlock - 1) / kHubBlock;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t v0 = tile * kHubBlock + threadIdx.x;
-    const bool hub = v0 < n_vertices && vtx[v0].deg >= kHubDeg;
-    if (__syncthreads_count(hub) == 0) continue;
-    if (threadIdx.x == 0) n_hubs = 0;
+                                                              const int32_t* __restrict__ col,
+                                                              int32_t* __restrict__ hash,
+                                                              const int32_t* __restrict__ hubs,
+                                                              const unsigned int* __restrict__ n_hubs_ptr) {
+  const unsigned int n_hubs = *n_hubs_ptr;
+  for (unsigned int h = blockIdx.x; h < n_hubs; h += gridDim.x) {
+    const int64_t v = hubs[h];
+    const uint32_t deg = vtx[v].deg, base = vtx[v].base;
+    const uint32_t nb = n2v_hash_nbuckets(deg);
+    int32_t* table = hash + static_cast<size_t>(n2v_hash_base(base, static_cast<uint32_t>(v))) * N2V_HASH_SLOTS;
+    for (uint32_t i = threadIdx.x; i < nb * N2V_HASH_SLOTS; i += kHubBlock) table[i] = N2V_HASH_EMPTY;
     __syncthreads();
-    if (hub) hubs[atomicAdd(&n_hubs, 1)] = threadIdx.x;
-    __syncthreads();
-    for (int h = 0; h < n_hubs; ++h) {
-      const int64_t v = tile * kHubBlock + hubs[h];
-      const uint32_t deg = vtx[v].deg, base = vtx[v].base;
-      const uint32_t nb = n2v_hash_nbuckets(deg);
-      int32_t* table = hash + static_cast<size_t>(n2v_hash_base(base, static_cast<uint32_t>(v))) * N2V_HASH_SLOTS;
-      for (uint32_t i = threadIdx.x; i < nb * N2V_HASH_SLOTS; i += kHubBlock) table[i] = N2V_HASH_EMPTY;
-      __syncthreads();
-      const int32_t* c = col + base;
-      for (uint32_t i = threadIdx.x; i < deg; i += kHubBlock) {
-        const int32_t x = c[i];
-        if (i > 0 && c[i - 1] == x) continue;
-        insert_neighbour(table, nb, x);
-      }
+    const int32_t* c = col + base;
+    for (uint32_t i = threadIdx.x; i < deg; i += kHubBlock) {
+      const int32_t x = c[i];
+      if (i > 0 && c[i - 1] == x) continue;
+      insert_neighbour(table, nb, x);
     }
-    __syncthreads();
   }
 }
 
@@ -111,10 +107,20 @@ extern "C" int n2v_hash_build(n2v_vertex_t* vtx, const int32_t* col, int64_t n_v
   N2V_CHECK_ARG(n_buckets_cap >= n2v_hash_buckets_bound(n_arcs, n_vertices) && n_buckets_cap < (int64_t(1) << 32),
                 "n2v_hash_build: bucket capacity %lld out of range", static_cast<long long>(n_buckets_cap));
   N2V_CHECK_ARG((reinterpret_cast<uintptr_t>(hash) & 31) == 0, "n2v_hash_build: hash must be 32-byte aligned");
-  fill_buckets<<<grid_for(n_vertices), kBlock, 0, stream>>>(vtx, col, n_vertices, hash);
-  const int64_t n_tiles = (n_vertices + kHubBlock - 1) / kHubBlock;
-  const int64_t hub_cap = int64_t(n2v::sm_count()) * 2;
-  fill_hub_buckets<<<static_cast<int>(n_tiles < hub_cap ? n_tiles : hub_cap), kHubBlock, 0, stream>>>(vtx, col, n_vertices, hash);
+  // device scratch: the hub count, then the hub list (at most n_arcs / kHubDeg entries)
+  const int64_t max_hubs = n_arcs / kHubDeg + 1;
+  unsigned int* d_nhubs = nullptr;
+  N2V_CUDA(n2v::scratch_alloc(reinterpret_cast<void**>(&d_nhubs), 8 + sizeof(int32_t) * static_cast<size_t>(max_hubs), stream));
+  N2V_CUDA(cudaMemsetAsync(d_nhubs, 0, 8, stream));
+  int32_t* d_hubs = reinterpret_cast<int32_t*>(d_nhubs + 2);
+  fill_buckets<<<grid_for(n_vertices), kBlock, 0, stream>>>(vtx, col, n_vertices, hash, d_hubs, d_nhubs);
   N2V_LAUNCH_OK();
+  if (n_arcs >= kHubDeg) {
+    const int64_t hub_cap = int64_t(n2v::sm_count()) * 2;
+    fill_hub_buckets<<<static_cast<int>(max_hubs < hub_cap ? max_hubs : hub_cap), kHubBlock, 0, stream>>>(
+        vtx, col, hash, d_hubs, d_nhubs);
+    N2V_LAUNCH_OK();
+  }
+  N2V_CUDA(cudaFreeAsync(d_nhubs, stream));
   return N2V_OK;
 }

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from oracle import clib, ref_walk
-from tests.helpers import chi_square_ok, pack_arcs
+from tests.helpers import chi_square_ok, graph_flags, pack_arcs
 
 pytestmark = pytest.mark.gpu
 
@@ -161,6 +161,51 @@ def test_alias_build_on_an_all_unit_graph_is_the_arc_parallel_path_and_bit_exact
             assert np.array_equal(h["wsum"][deg > 0], wsum[deg > 0]) and not h["wsum"][deg == 0].any()
             if w is not off:
                 assert (h["thr"] == 0xFFFFFFFF).all() and not h["alias"].any()
+
+
+def test_symmetric_flag_under_single_arc_mutations(n2v):
+    """K0's SYMMETRIC flag selects the walk's fast fold, so it has to be exact.  The check searches from one
+    side of every mirrored pair only (the arc whose head has the smaller (degree, id)) and balances the
+    counts; here a symmetric weighted graph with a hub, equal-degree neighbours and a self-loop is mutated
+    one arc at a time and the flags are compared with a set-based check on the host."""
+    rng = np.random.default_rng(21)
+    n = 400
+    a = rng.integers(0, n, 3000); b = rng.integers(0, n, 3000)
+    hub = np.full(350, 7); leaves = rng.permutation(n)[:350]
+    a, b = np.concatenate([a, hub, [5, 9]]), np.concatenate([b, leaves, [5, 10]])      # (5,5): a self-loop; (9,10)
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    key, idx = np.unique(lo.astype(np.int64) << 32 | hi, return_index=True)
+    lo, hi = lo[idx], hi[idx]
+    w = rng.uniform(0.5, 2.0, len(lo))
+    loop = lo == hi
+    src = np.concatenate([lo, hi[~loop]]); dst = np.concatenate([hi, lo[~loop]]); ws = np.concatenate([w, w[~loop]])
+
+    def flags_of(s, d, x):
+        g = n2v.graph.DeviceGraph.from_arcs(s, d, x, n_vertices=n)
+        row_ptr, col, wsorted, _ = clib.csr_from_arcs(s, d, x, n)
+        want = graph_flags(row_ptr, col, wsorted)
+        assert g.flags == want, (g.flags, want)
+        return g.flags
+
+    SYM = n2v.lib.GRAPH_SYMMETRIC
+    assert flags_of(src, dst, ws) & SYM
+    deg = np.bincount(src, minlength=n)
+    picks = list(rng.integers(0, len(src), 12))
+    picks += [int(np.flatnonzero(src == 7)[0]), int(np.flatnonzero(dst == 7)[0])]              # hub-side and leaf-side arcs
+    same = np.flatnonzero((deg[src] == deg[dst]) & (src != dst))
+    picks += [int(same[0]), int(same[-1])] if len(same) else []                               # the (degree, id) tie-break
+    for i in picks:
+        if src[i] == dst[i]:
+            continue
+        keep = np.ones(len(src), dtype=bool); keep[i] = False
+        assert not flags_of(src[keep], dst[keep], ws[keep]) & SYM                             # a mirror is missing
+        w2 = ws.copy(); w2[i] = np.nextafter(w2[i], 3.0)
+        assert not flags_of(src, dst, w2) & SYM                                               # a mirror weighs an ulp more
+    free = [(u, v) for u in range(20) for v in range(20, 40) if u != v and not ((src == u) & (dst == v)).any()][:3]
+    for u, v in free:                                                                         # a one-way arc
+        assert not flags_of(np.append(src, u), np.append(dst, v), np.append(ws, 1.0)) & SYM
+        assert flags_of(np.append(src, [u, v]), np.append(dst, [v, u]), np.append(ws, [1.5, 1.5])) & SYM
+    assert flags_of(np.append(src, 11), np.append(dst, 11), np.append(ws, 1.0)) & SYM         # one more self-loop
 
 
 def test_bad_vertex_ids_raise_and_do_not_poison_the_context(n2v):
