@@ -3,6 +3,12 @@ walks bit-identical to the replicated graph's, and data-parallel SGNS must end w
 tables on every rank.  Prints MULTI_GPU_CHECK OK on rank 0.
 
   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_check.py
+
+N2V_CHECK_ONE_GPU=1 runs the same check with every rank on cuda:0 (a single-GPU box): the parts are still
+separate VMM allocations in separate processes, exported as fds and mapped by the peer, and the kernel's
+MULTI variant still dereferences parts[v / part_size] -- only the wire is missing.  NCCL refuses two ranks
+on one device, so the plumbing runs over gloo there (all_reduce / broadcast on device tensors; the one
+all_gather is staged through the host).
 """
 import os
 import sys
@@ -17,9 +23,21 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
-    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
-    dist.init_process_group("nccl", device_id=dev)
+    one_gpu = os.environ.get("N2V_CHECK_ONE_GPU") == "1"
+    index = 0 if one_gpu else int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(index)
+    dev = torch.device("cuda", index)
+    if one_gpu:
+        dist.init_process_group("gloo")
+        gather = dist.all_gather_into_tensor
+
+        def staged_all_gather(out, inp, group=None):     # gloo has no all_gather on device tensors
+            host = torch.empty(out.shape, dtype=out.dtype)
+            gather(host, inp.cpu(), group=group)
+            out.copy_(host)
+        dist.all_gather_into_tensor = staged_all_gather
+    else:
+        dist.init_process_group("nccl", device_id=dev)
     from node2vec_b200 import dist as n2v_dist, synth
     from node2vec_b200.graph import DeviceGraph, PartitionedGraph
     from node2vec_b200.sgns import Word2Vec
