@@ -148,8 +148,9 @@ def trim_index(
     ``indexed=True`` returns the trimmed frame untouched and ``None``.
     Frames whose ``src`` / ``dst`` are integer names are trimmed, indexed and (``directed=False``)
     mirrored ON THE DEVICE when a GPU is present -- K5 / K6, one H2D of the columns in, the frames the
-    reference returns out, row for row; string names are first replaced by their rank among the sorted
-    distinct names on the host (one pass), the row-level work is the same device path.
+    reference returns out, row for row; string names go to the device as raw UTF-8 bytes (one Arrow buffer
+    pair), K6 matches them byte for byte and only the V distinct names come back to be sorted on the host
+    (the reference's partition order), the row-level work is the same device path.
     Tuples of device tensors ``(src, dst[, weight])`` (integer names) never leave the GPU and return
     ``((src, dst, weight), (vertex_id, vertex_name))`` tensors.  Keyword-only ``dense_ids=True`` numbers
     vertices 0..V-1 in first-occurrence order instead of the reference's sparse positions."""
@@ -227,8 +228,9 @@ def _frame_name_keys(df: pd.DataFrame, device=None):
 def _index_graph_frame_on_device(df: pd.DataFrame, directed, max_out_deg=None, random_seed=None):
     """``index_graph_pandas`` (and, with ``max_out_deg`` given, the partition + trim step before it)
     for a pandas frame with the row-level work on the GPU (K5 trimming, K6 first-occurrence ids and
-    de-duplication): one H2D of the columns, the reference's two frames back.  Strings never go to the
-    device: they are replaced by ranks first and mapped back in the name table.
+    de-duplication): one H2D of the columns, the reference's two frames back.  String names are replaced by
+    order-preserving ranks first (``_frame_name_keys``: found on the device from the raw bytes) and mapped
+    back in the name table.
     Returns None when the names cannot be ranked (mixed types): the caller falls back to pandas."""
     from .preprocess import index_graph_device, trim_partitioned
     dev = torch.device("cuda", torch.cuda.current_device())
