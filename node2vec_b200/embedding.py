@@ -63,26 +63,22 @@ class Node2VecGensim(Node2VecBase):
         vector_size: Optional[int] = None,
         random_seed: Optional[int] = None,
     ) -> None:
-        logging.info("__init__(): preprocssing ...")
         super().__init__()
-        self.walks = df_walks
-        self.name_id = name_id
+        self.walks, self.name_id = df_walks, name_id
         self.model: Optional[Word2Vec] = None
-
-        for param in GENSIM_PARAMS:
-            if param not in w2v_params:
-                w2v_params[param] = GENSIM_PARAMS[param]
-        w2v_params["seed"] = random_seed if random_seed else int(time.time()) // 60
-        if window_size is not None:
-            if window_size < 5 or window_size > 30:
-                raise ValueError(f"Inappropriate context window size {window_size}!")
-            w2v_params["window"] = window_size
-        if vector_size is not None:
-            if vector_size < 32 or vector_size > 1024:
-                raise ValueError(f"Inappropriate vector dimension {vector_size}!")
-            w2v_params["size"] = vector_size
-        logging.info(f"__init__(): w2v params: {w2v_params}")
+        # the caller's dict IS the parameter set (the reference merges into it in place, embedding.py:105-107)
+        for key, default in GENSIM_PARAMS.items():
+            w2v_params.setdefault(key, default)
+        w2v_params["seed"] = random_seed or int(time.time()) // 60        # None / 0: minutes since the epoch (:108)
+        for value, lo, hi, key, what in ((window_size, 5, 30, "window", "context window size"),
+                                         (vector_size, 32, 1024, "size", "vector dimension")):
+            if value is None:
+                continue
+            if not lo <= value <= hi:
+                raise ValueError(f"Inappropriate {what} {value}!")
+            w2v_params[key] = value
         self.w2v_params = w2v_params
+        logging.info("Node2VecGensim: word2vec parameters %s", w2v_params)
 
     def _sentences(self):
         dev = getattr(self.walks, "walks_device", None)

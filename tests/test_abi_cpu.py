@@ -327,3 +327,29 @@ def test_walk_matrix_inputs_host_logic():
     with pytest.raises(ValueError):
         _walk_matrix([[1, 2, 3], [4, 5]], cpu)
     assert neg_top_entries(65536) == 0 and neg_top_entries(65537) == 9 and neg_top_entries(1 << 26) == (1 << 26) // NEG_CHUNK
+
+
+def test_node2vec_gensim_constructor_contract_needs_no_gpu():
+    """embedding.py:75-118 of the reference: defaults merged into the CALLER's dict, seed = random_seed or
+    minutes since the epoch, window in [5, 30] and size in [32, 1024] else ValueError -- raised after the
+    earlier keys were already written, as the reference does."""
+    import pandas as pd
+    from node2vec_b200.constants import GENSIM_PARAMS
+    from node2vec_b200.embedding import Node2VecGensim
+    df = pd.DataFrame({"src": [0], "walk": [[0, 1]]})
+    p = {}
+    m = Node2VecGensim(df, p, window_size=5, vector_size=32, random_seed=7)
+    assert m.w2v_params is p and p["seed"] == 7 and p["window"] == 5 and p["size"] == 32
+    assert all(k in p for k in GENSIM_PARAMS)
+    p2 = {"iter": 3}
+    Node2VecGensim(df, p2)
+    assert p2["iter"] == 3 and p2["seed"] > 0 and p2["window"] == GENSIM_PARAMS["window"]
+    for kw in ({"window_size": 4}, {"window_size": 31}, {"vector_size": 31}, {"vector_size": 1025}):
+        with pytest.raises(ValueError):
+            Node2VecGensim(df, {}, **kw)
+    q = {}
+    with pytest.raises(ValueError):
+        Node2VecGensim(df, q, window_size=6, vector_size=8)
+    assert q["window"] == 6 and "seed" in q and "size" in q
+    with pytest.raises(ValueError):
+        m.embedding()                                   # before fit()
